@@ -1,0 +1,77 @@
+"""Generate tests/golden/* in the BUILD CONTAINER (needs /root/reference; never run on the GPU box).
+
+    python tests/golden/make_golden.py
+
+What is pinned by what
+  av2_fixture_clouds.npz   xyz of the reference's own test clouds OSF/assets/tests/test_pc{0,1}.npy
+                           (fp16-quantised in the reference, stored losslessly as float16) + the
+                           reference's recorded known answer, Chamfer loss 0.1710
+                           (OSF/assets/tests/chamferdis_speed_test.py:113-126)
+  deflowpp_n*.npz          outputs of the reference's OWN `src.models.DeFlowPP` class (imported from
+                           /root/reference through oracle/ref_shims.py) on seeded synthetic triples with
+                           himo_b200.weights.synth_deflowpp_state_dict(seed) loaded strictly
+  neural_prior_*.npz       outputs / gradients of the reference's `Neural_Prior` + `EarlyStopping`
+                           trace (OSF/src/models/basic/nsfp_module.py)
+  himo_compdis_*.npz       HiMo `flow2compDis` / `ego_pts_mask` (utils/__init__.py:26-47) outputs
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from himo_b200 import frames, weights  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+
+
+def fixture_clouds():
+    base = os.path.join(ref_shims.OSF_ROOT, "assets", "tests")
+    pc0 = np.load(os.path.join(base, "test_pc0.npy"))[:, :3]
+    pc1 = np.load(os.path.join(base, "test_pc1.npy"))[:, :3]
+    assert (pc0.astype(np.float16).astype(np.float32) == pc0).all()
+    assert (pc1.astype(np.float16).astype(np.float32) == pc1).all()
+    np.savez_compressed(os.path.join(HERE, "av2_fixture_clouds.npz"), pc0=pc0.astype(np.float16),
+                        pc1=pc1.astype(np.float16), chamfer_known_answer=np.float32(0.1710))
+
+
+def deflowpp(models, n, seed, kind):
+    sd = weights.synth_deflowpp_state_dict(seed)
+    net = models.DeFlowPP().eval()
+    net.load_state_dict(sd, strict=True)
+    tr = frames.lidar_triple(n, seed) if kind == "lidar" else frames.uniform_triple(n, seed)
+    if kind == "uniform":  # exercise the NaN-padding path of DynamicVoxelizer (encoder.py:576-578)
+        tr["pc0"][5::97] = np.nan
+    batch = {k: torch.from_numpy(tr[k])[None] for k in ("pc0", "pc1", "pch1")}
+    batch.update({k: [torch.from_numpy(tr[k])] for k in ("pose0", "pose1", "poseh1")})
+    torch.set_num_threads(1)  # fixed reduction order inside the CPU convolutions
+    with torch.no_grad():
+        out = net(batch)
+    np.savez_compressed(
+        os.path.join(HERE, f"deflowpp_{kind}_n{n}_s{seed}.npz"),
+        pc0=tr["pc0"], pc1=tr["pc1"], pch1=tr["pch1"], pose0=tr["pose0"], pose1=tr["pose1"],
+        poseh1=tr["poseh1"], weight_seed=np.int64(seed),
+        flow=out["flow"][0].numpy(), pose_flow=out["pose_flow"][0].numpy(),
+        pc0_valid_point_idxes=out["pc0_valid_point_idxes"][0].numpy(),
+        pc1_valid_point_idxes=out["pc1_valid_point_idxes"][0].numpy(),
+        pch1_valid_point_idxes=out["pch1_valid_point_idxes"][0].numpy())
+
+
+def main():
+    assert ref_shims.reference_available(), "needs /root/reference"
+    fixture_clouds()
+    models = ref_shims.import_models()
+    deflowpp(models, 2000, 11, "lidar")
+    deflowpp(models, 3000, 12, "uniform")
+    for name in sorted(os.listdir(HERE)):
+        if name.endswith(".npz"):
+            print(name, os.path.getsize(os.path.join(HERE, name)))
+
+
+if __name__ == "__main__":
+    main()
