@@ -88,6 +88,45 @@ int himo_chamfer_backward(const float* pc0, int n0, const float* pc1, int n1, co
                           const int32_t* idx1, const float* grad_dist0, const float* grad_dist1,
                           float* grad_pc0, float* grad_pc1, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * H4  dense convolution of the SeFlow++ backbone (tcgen05 implicit GEMM) and 2x bilinear upsample
+ * replaces: the ATen/cuDNN work behind nn.Conv2d (+ BatchNorm2d + GELU) in
+ *           ConvWithNorms.forward (OSF/src/models/basic/__init__.py:76-94) and
+ *           UpsampleSkip.forward / decoder_step4 (OSF/src/models/basic/unet.py:18-35,130),
+ *           i.e. every layer of UNetThreeFrame.forward (unet.py:131-166).
+ * Activations are NHWC bf16 "planes": plane 0 = bf16(x), optional plane 1 = bf16(x - plane0)
+ * (split-bf16; two planes give fp32-class products on the bf16 tensor cores).
+ *   in      [in_planes][H_in][W_in][Cin_total] bf16; the conv reads channels
+ *           [cin_off + g*cin_group_stride, +Cin) for group g (groups = frames sharing weights)
+ *   wgt     [in_planes][Cout][ksize*ksize*Cin] bf16, K index = (ky*ksize + kx)*Cin + ci
+ *   bias    [Cout] f32 or NULL (BatchNorm folded in by the host)
+ *   out     NHWC, channels [cout_off + g*cout_group_stride, +Cout) of Cout_total; bf16 planes
+ *           (out_planes 1|2) or fp32 (out_fp32 = 1)
+ *   ksize 1|3 (padding ksize/2), stride 1|2, act 0 none | 1 exact-erf GELU
+ */
+typedef struct himo_conv_desc {
+  const void* in;
+  int in_planes;
+  long long in_plane_stride; /* elements between input planes */
+  int H_in, W_in, Cin_total, cin_off, Cin;
+  const void* wgt;
+  const float* bias;
+  int Cout, ksize, stride;
+  void* out;
+  int out_planes;
+  long long out_plane_stride;
+  int Cout_total, cout_off;
+  int out_fp32, act;
+  int n_groups, cin_group_stride, cout_group_stride;
+} himo_conv_desc;
+int himo_conv2d_nhwc(const himo_conv_desc* desc, void* stream);
+/* replaces: F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) of
+ *           BilinearDecoder.forward (OSF/src/models/basic/unet.py:7-16); in [h][w][c] planes ->
+ *           channels [cout_off, +c) of out [2h][2w][Cout_total] planes. */
+int himo_upsample2x_nhwc(const void* in, int in_planes, long long in_plane_stride, int h, int w, int c,
+                         void* out, int out_planes, long long out_plane_stride, int Cout_total,
+                         int cout_off, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

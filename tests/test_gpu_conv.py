@@ -1,0 +1,75 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution against torch's fp32 CPU conv2d (the op
+the reference's ConvWithNorms / UpsampleSkip call).  Tolerances: split-bf16 (2 planes) is an fp32-class
+path -> 2e-5 relative to the output scale; single-plane bf16 -> 2e-2."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from himo_b200 import conv
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(H, W, cin, cout, ksize, stride, planes, act=0, out_fp32=False, groups=1, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(groups, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, ksize, ksize, generator=g) / np.sqrt(cin * ksize * ksize)
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(x, w, b, stride=stride, padding=ksize // 2)
+    if act:
+        ref = F.gelu(ref)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    # NHWC with the groups laid side by side in the channel dimension (frame-major slices)
+    x_nhwc = x.permute(2, 3, 0, 1).reshape(H, W, groups * cin).contiguous()
+    xp = conv.split_planes(x_nhwc.cuda(), planes)
+    wp = conv.pack_conv_weight(w, planes).cuda()
+    if out_fp32:
+        out = torch.full((Ho, Wo, groups * cout), float("nan"), device="cuda")
+    else:
+        out = torch.zeros((2, Ho, Wo, groups * cout), dtype=torch.bfloat16, device="cuda")
+    conv.conv2d_nhwc(xp, wp, b.cuda(), out, ksize=ksize, stride=stride, act=act, cin=cin, n_groups=groups,
+                     cin_group_stride=cin, cout_group_stride=cout)
+    torch.cuda.synchronize()
+    got = out if out_fp32 else conv.merge_planes(out)
+    got = got.cpu().reshape(Ho, Wo, groups, cout).permute(2, 3, 0, 1)
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item() / scale
+    return err
+
+
+@pytest.mark.parametrize("H,W,cin,cout,ksize,stride", [
+    (128, 128, 64, 64, 3, 1),      # encoder_step_1.x shape class, BN=64
+    (64, 128, 32, 64, 3, 2),       # first layer: Cin=32, stride 2 (TMA element stride)
+    (128, 128, 96, 96, 1, 1),      # 1x1 (u3), BN=96
+    (64, 64, 128, 128, 3, 1),      # W=64 -> 64x2 tiles, BN=128
+    (128, 128, 64, 128, 3, 2),     # stride 2 down to W=64
+    (128, 128, 192, 96, 3, 1),     # u4 of decoder_step3: Cin=192
+    (32, 128, 256, 256, 3, 1),     # two N tiles of 128
+])
+def test_conv_split_bf16_matches_fp32(H, W, cin, cout, ksize, stride):
+    err = _run(H, W, cin, cout, ksize, stride, planes=2)
+    assert err < 2e-5, err
+
+
+def test_conv_gelu_fp32_out_and_groups():
+    assert _run(128, 128, 64, 64, 3, 1, planes=2, act=1) < 2e-5
+    assert _run(128, 128, 96, 96, 3, 1, planes=2, out_fp32=True) < 2e-5
+    assert _run(128, 128, 32, 64, 3, 2, planes=2, act=1, groups=3) < 2e-5
+
+
+def test_conv_single_plane_bf16():
+    assert _run(128, 128, 64, 64, 3, 1, planes=1) < 2e-2
+    assert _run(128, 128, 192, 96, 3, 1, planes=1, act=1) < 2e-2
+
+
+def test_upsample2x_matches_interpolate():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 64, 32, 48, generator=g)
+    ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)[0].permute(1, 2, 0)
+    xp = conv.split_planes(x[0].permute(1, 2, 0).contiguous().cuda(), 2)
+    out = torch.zeros((2, 64, 96, 128), dtype=torch.bfloat16, device="cuda")
+    conv.upsample2x_nhwc(xp, out, cout_off=64)
+    got = conv.merge_planes(out).cpu()
+    assert (got[:, :, :64] == 0).all()
+    np.testing.assert_allclose(got[:, :, 64:].numpy(), ref.numpy(), rtol=0, atol=3e-5)
