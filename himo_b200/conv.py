@@ -20,6 +20,7 @@ class ConvDesc(ctypes.Structure):
         ("out", c_void_p), ("out_planes", c_int), ("out_plane_stride", c_longlong),
         ("Cout_total", c_int), ("cout_off", c_int), ("out_fp32", c_int), ("act", c_int),
         ("n_groups", c_int), ("cin_group_stride", c_int), ("cout_group_stride", c_int),
+        ("acc_scale", ctypes.c_float),
     ]
 
 
@@ -30,28 +31,46 @@ _lib.register("himo_upsample2x_nhwc", c_int,
 
 
 def split_planes(x: torch.Tensor, planes: int) -> torch.Tensor:
-    """fp32 [...] -> bf16 [planes, ...]: plane0 = bf16(x), plane1 = bf16(x - plane0)."""
-    hi = x.to(torch.bfloat16)
+    """fp32 [...] -> 16-bit [planes, ...] stored in a bf16-typed tensor.
+    planes == 1: bf16(x).  planes == 2: split fp16 -- plane0 = fp16(x), plane1 = fp16(x - plane0),
+    both bit-cast into the bf16 storage (11 + 11 mantissa bits)."""
     if planes == 1:
-        return hi.unsqueeze(0).contiguous()
-    lo = (x - hi.float()).to(torch.bfloat16)
-    return torch.stack([hi, lo], 0).contiguous()
+        return x.to(torch.bfloat16).unsqueeze(0).contiguous()
+    hi = x.to(torch.float16)
+    lo = (x - hi.float()).to(torch.float16)
+    return torch.stack([hi, lo], 0).contiguous().view(torch.bfloat16)
 
 
 def merge_planes(p: torch.Tensor) -> torch.Tensor:
-    return p.float().sum(0)
+    if p.shape[0] == 1:
+        return p[0].float()
+    h = p.contiguous().view(torch.float16)
+    return h[0].float() + h[1].float()
 
 
-def pack_conv_weight(w: torch.Tensor, planes: int) -> torch.Tensor:
-    """[Cout, Cin, kh, kw] fp32 -> [planes, Cout, kh*kw*Cin] bf16, K index = (ky*kw + kx)*Cin + ci."""
+def weight_prescale(w: torch.Tensor, planes: int) -> float:
+    """Power of two that brings max|w| to [256, 512) in split mode (keeps the low fp16 plane of the
+    weights in the normal range); 1 for the single-plane bf16 mode."""
+    if planes == 1:
+        return 1.0
+    m = float(w.abs().max())
+    if m == 0.0:
+        return 1.0
+    import math
+    return 2.0 ** (8 - math.floor(math.log2(m)))
+
+
+def pack_conv_weight(w: torch.Tensor, planes: int, prescale: float = 1.0) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] fp32 -> [planes, Cout, kh*kw*Cin] 16-bit, K index = (ky*kw + kx)*Cin + ci."""
     cout, cin, kh, kw = w.shape
-    k = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
+    k = (w * prescale).permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
     return split_planes(k, planes)
 
 
 def conv2d_nhwc(x_planes: torch.Tensor, w_planes: torch.Tensor, bias, out: torch.Tensor, *, ksize: int,
                 stride: int = 1, act: int = 0, cin_off: int = 0, cin: int | None = None, cout_off: int = 0,
-                n_groups: int = 1, cin_group_stride: int = 0, cout_group_stride: int = 0) -> None:
+                n_groups: int = 1, cin_group_stride: int = 0, cout_group_stride: int = 0,
+                acc_scale: float = 1.0) -> None:
     """x_planes [P,H,W,Cin_total] bf16; w_planes [P,Cout,K] bf16; out [Po,Ho,Wo,Cout_total] bf16 or
     [Ho,Wo,Cout_total] fp32 (written in place)."""
     P, H, W, Ct = x_planes.shape
@@ -70,7 +89,7 @@ def conv2d_nhwc(x_planes: torch.Tensor, w_planes: torch.Tensor, bias, out: torch
         d.out_fp32 = 0; d.out_planes = out.shape[0]
         d.out_plane_stride = out.shape[1] * out.shape[2] * out.shape[3]
         d.Cout_total = out.shape[3]
-    d.cout_off = cout_off; d.act = act
+    d.cout_off = cout_off; d.act = act; d.acc_scale = acc_scale
     d.n_groups = n_groups; d.cin_group_stride = cin_group_stride; d.cout_group_stride = cout_group_stride
     dev = x_planes.device
     with torch.cuda.device(dev):

@@ -6,19 +6,20 @@
 //
 // Formulation: D[pixels, Cout] = sum over taps (ky,kx) and input-channel chunks of
 //              A_tap[pixels, BK] * W_tap[Cout, BK]^T
-//  * activations live in HBM as NHWC bf16 "planes": plane 0 = bf16(x), plane 1 = bf16(x - plane0).
-//    With two planes the kernel issues three MMAs per k-step (hi*hi + hi*lo + lo*hi, fp32 accumulate
-//    in TMEM): the product error drops to ~2^-17 relative, which is what the reference's fp32 path
-//    needs for the <=1e-4 flow parity; with one plane it is a plain bf16 GEMM.
+//  * activations live in HBM as NHWC 16-bit "planes".  Two planes = split fp16: plane 0 = fp16(x),
+//    plane 1 = fp16(x - plane0) (11 + 11 mantissa bits); the kernel then issues three MMAs per k-step
+//    (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM; the dropped lo*lo term is ~2^-22 relative), which
+//    is what the reference's fp32 path needs for the <=1e-4 flow parity.  Weights are pre-scaled by a
+//    power of two (undone exactly in the epilogue, `acc_scale`) so that their low plane stays in
+//    fp16's normal range.  One plane = plain bf16 GEMM (the speed mode).
 //  * no im2col: for every tap the A tile of 128 output pixels x BK channels is ONE 4-D TMA box
 //    (channels, x, y, plane) fetched at (x0*stride + kx - pad, y0*stride + ky - pad); TMA's
 //    out-of-bounds zero fill is the convolution padding and its element stride is the conv stride.
 //  * tiles land in shared memory in the 64-byte-swizzled K-major layout tcgen05.mma consumes;
 //    accumulators stay in tensor memory; one thread issues the MMAs; four warps drain TMEM through
 //    tcgen05.ld and fuse bias (folded BN), exact-erf GELU and the hi/lo split into the store.
-//  * warp roles: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue
-//    (TMEM lane quadrant = warp & 3).  Two CTAs are co-resident per SM so one tile's epilogue
-//    overlaps the other's MMAs.
+//  * warp roles: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-9 epilogue
+//    (TMEM lane quadrant = warp & 3, two warps per quadrant split the columns).
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -28,7 +29,8 @@
 namespace himo {
 
 constexpr int kConvBM = 128;
-constexpr int kConvThreads = 192;
+constexpr int kConvEpiWarps = 8;
+constexpr int kConvThreads = 64 + kConvEpiWarps * 32;
 
 struct ConvParams {
   int tiles_x, tiles_y, n_tiles_n, n_groups;
@@ -41,6 +43,8 @@ struct ConvParams {
   long long out_plane_stride;
   int W_out, Cout_total, cout_off, cout_group_stride;
   int act, out_fp32;
+  float acc_scale;
+  int flush_iters;
 };
 
 __device__ __forceinline__ float gelu_erf(float v) {
@@ -56,21 +60,35 @@ struct ConvSmem {
   static constexpr int kTotal = kBarOffset + 256 + BN * 4 + 1024;  // + barriers + bias + align slack
 };
 
+// Accumulation scheme (split mode, P == 2).  tcgen05 adds every MMA into the fp32 TMEM accumulator
+// with truncation, so a long accumulation chain drifts by ~0.5 ulp per MMA (measured: error grows
+// linearly with K).  To stay fp32-class:
+//   * the small cross products hi*lo + lo*hi go to their own accumulator ("cross"), so they never
+//     round the large hi*hi sum;
+//   * the hi*hi chain is cut every `flush_iters` k-iterations: the MMA warp ping-pongs between two
+//     "main" accumulators and the epilogue warps drain the finished one into fp32 registers
+//     (round-to-nearest adds) while the tensor core fills the other.
+// TMEM columns: main0 [0,BN), main1 [BN,2BN), cross [2BN,3BN).  Single-plane mode uses main0 only.
 template <int BN, int BK, int P, int STAGES>
 __global__ void __launch_bounds__(kConvThreads)
 k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const ConvParams p) {
   using S = ConvSmem<BN, BK, P, STAGES>;
-  constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr int kUsedCols = P == 2 ? 3 * BN : BN;
+  constexpr int kTmemCols = kUsedCols <= 32 ? 32 : kUsedCols <= 64 ? 64 : kUsedCols <= 128 ? 128
+                            : kUsedCols <= 256 ? 256 : 512;
   constexpr int kRowBytes = BK * 2;
-  constexpr int kProducts = P == 2 ? 3 : 1;
+  constexpr int kHalf = BN / 2;            // columns owned by one epilogue thread
+  constexpr int kGroups = kHalf / 16;
+  static_assert(kHalf % 16 == 0, "BN must be a multiple of 32");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + S::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_full_bar + 1);
+  uint64_t* acc_full_bar = empty_bar + STAGES;     // [2]
+  uint64_t* acc_empty_bar = acc_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr_smem = (uint32_t*)(acc_empty_bar + 2);
   float* bias_s = (float*)(smem + S::kBarOffset + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -83,6 +101,8 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int g = t;
   const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BN;
   const int k_iters = p.taps * p.k_chunks;
+  const int flush = P == 2 ? p.flush_iters : k_iters;
+  const int n_chunks = (k_iters + flush - 1) / flush;
 
   if (warp == 0 && lane == 0) {
     umma::tma_prefetch_desc(&tmA);
@@ -91,12 +111,15 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       umma::mbar_init(&full_bar[s], 1);
       umma::mbar_init(&empty_bar[s], 1);
     }
-    umma::mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      umma::mbar_init(&acc_full_bar[b], 1);
+      umma::mbar_init(&acc_empty_bar[b], kConvEpiWarps);
+    }
     umma::fence_barrier_init();
   } else if (warp == 1) {
     umma::tmem_alloc(tmem_ptr_smem, kTmemCols);
   } else if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+    for (int i = threadIdx.x - 64; i < BN; i += kConvEpiWarps * 32) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
   }
   umma::tc_fence_before();
   __syncthreads();
@@ -128,77 +151,115 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = umma::idesc_bf16_f32(kConvBM, BN);
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        umma::mbar_wait(&full_bar[s], ph);
-        umma::tc_fence_after();
-        const uint32_t a_addr = umma::smem_u32(smem + s * S::kStageBytes);
-        const uint32_t b_addr = a_addr + P * S::kABytes;
-        uint64_t adesc[P], bdesc[P];
-#pragma unroll
-        for (int pl = 0; pl < P; ++pl) {
-          adesc[pl] = umma::smem_desc_kmajor<kRowBytes>(a_addr + pl * S::kABytes);
-          bdesc[pl] = umma::smem_desc_kmajor<kRowBytes>(b_addr + pl * S::kBBytes);
+      // kind::f16 format codes: 0 = fp16 (split mode, both planes), 1 = bf16 (single-plane mode)
+      constexpr uint32_t kFmt = P == 2 ? 0u : 1u;
+      constexpr uint32_t idesc = umma::idesc_f16kind_f32(kConvBM, BN, kFmt, kFmt);
+      const uint32_t tmem_cross = tmem_base + 2 * BN;
+      int it = 0;
+      for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        const int buf = chunk & 1;
+        const uint32_t tmem_main = tmem_base + buf * BN;
+        if (P == 2) {   // wait until the epilogue has drained this accumulator (2 chunks ago)
+          umma::mbar_wait(&acc_empty_bar[buf], ((chunk >> 1) & 1) ^ 1);
+          umma::tc_fence_after();
         }
+        const int it_begin = it, it_end = min(it + flush, k_iters);
+        for (; it < it_end; ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          umma::mbar_wait(&full_bar[s], ph);
+          umma::tc_fence_after();
+          const uint32_t a_addr = umma::smem_u32(smem + s * S::kStageBytes);
+          const uint32_t b_addr = a_addr + P * S::kABytes;
+          uint64_t adesc[P], bdesc[P];
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t koff = (uint64_t)(k * 32 >> 4);  // 16 bf16 = 32 bytes along K
-#pragma unroll
-          for (int pr = 0; pr < kProducts; ++pr) {
-            // products: hi*hi, hi*lo, lo*hi (lo*lo ~ 2^-18 relative is dropped)
-            const int pa = pr == 2 ? 1 : 0, pb = pr == 1 ? 1 : 0;
-            umma::mma_bf16_ss(tmem_base, adesc[pa] + koff, bdesc[pb] + koff, idesc,
-                              (it | k | pr) != 0 ? 1u : 0u);
+          for (int pl = 0; pl < P; ++pl) {
+            adesc[pl] = umma::smem_desc_kmajor<kRowBytes>(a_addr + pl * S::kABytes);
+            bdesc[pl] = umma::smem_desc_kmajor<kRowBytes>(b_addr + pl * S::kBBytes);
           }
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t koff = (uint64_t)(k * 32 >> 4);  // 16 elements = 32 bytes along K
+            umma::mma_bf16_ss(tmem_main, adesc[0] + koff, bdesc[0] + koff, idesc,
+                              (it != it_begin || k != 0) ? 1u : 0u);
+            if (P == 2) {   // hi*lo + lo*hi (lo*lo ~ 2^-22 relative is dropped)
+              umma::mma_bf16_ss(tmem_cross, adesc[0] + koff, bdesc[P - 1] + koff, idesc, (it | k) != 0 ? 1u : 0u);
+              umma::mma_bf16_ss(tmem_cross, adesc[P - 1] + koff, bdesc[0] + koff, idesc, 1u);
+            }
+          }
+          umma::mma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
         }
-        umma::mma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
+        umma::mma_commit(&acc_full_bar[buf]);  // this chunk's accumulator (and all earlier MMAs) done
       }
-      umma::mma_commit(tmem_full_bar);     // accumulator complete -> epilogue
     }
   } else {
-    // ===================== epilogue (4 warps) =====================
-    umma::mbar_wait(tmem_full_bar, 0);
-    umma::tc_fence_after();
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;          // tile row = output pixel within the tile
+    // ===================== epilogue (8 warps: 2 per TMEM lane quadrant) =====================
+    const int q = warp & 3;                           // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;                 // which half of the BN columns
+    const int row = q * 32 + lane;                    // tile row = output pixel within the tile
+    const uint32_t lane_col = ((uint32_t)(q * 32) << 16) + (uint32_t)(half * kHalf);
+    float acc[kHalf];
+#pragma unroll
+    for (int j = 0; j < kHalf; ++j) acc[j] = 0.f;
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+      const int buf = chunk & 1;
+      umma::mbar_wait(&acc_full_bar[buf], (chunk >> 1) & 1);
+      umma::tc_fence_after();
+#pragma unroll
+      for (int gi = 0; gi < kGroups; ++gi) {
+        uint32_t r[16];
+        umma::tmem_ld_32x16(tmem_base + lane_col + (uint32_t)(buf * BN + gi * 16), r);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[gi * 16 + j] += __uint_as_float(r[j]);
+      }
+      if (P == 2) {
+        umma::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&acc_empty_bar[buf]);
+      }
+    }
+    if (P == 2) {   // the last acc_full commit also covers every cross-term MMA
+#pragma unroll
+      for (int gi = 0; gi < kGroups; ++gi) {
+        uint32_t r[16];
+        umma::tmem_ld_32x16(tmem_base + lane_col + (uint32_t)(2 * BN + gi * 16), r);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[gi * 16 + j] += __uint_as_float(r[j]);
+      }
+    }
     const int py = y0 + row / p.TW, px = x0 + row % p.TW;
     const long long pix = (long long)py * p.W_out + px;
-    const long long ch0 = (long long)p.cout_off + (long long)g * p.cout_group_stride + n0;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      umma::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      umma::tmem_ld_wait();
-      float v[32];
+    const long long ch0 = (long long)p.cout_off + (long long)g * p.cout_group_stride + n0 + half * kHalf;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]) + bias_s[c * 32 + j];
-        v[j] = p.act == 1 ? gelu_erf(x) : x;
+    for (int gi = 0; gi < kGroups; ++gi) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = __fmaf_rn(acc[gi * 16 + j], p.acc_scale, bias_s[half * kHalf + gi * 16 + j]);
+        v[j] = p.act == 0 ? x
+               : p.act == 1 ? gelu_erf(x)
+               : p.act == 2 ? __fdiv_rn(1.0f, 1.0f + expf(-x))     // torch.sigmoid
+                            : tanhf(x);                             // torch.tanh
       }
       if (p.out_fp32) {
-        float4* dst = (float4*)((float*)p.out + pix * p.Cout_total + ch0 + c * 32);
+        float4* dst = (float4*)((float*)p.out + pix * p.Cout_total + ch0 + gi * 16);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       } else {
-        __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * p.Cout_total + ch0 + c * 32;
-        uint32_t hi[16];
+        __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * p.Cout_total + ch0 + gi * 16;
+        const bool split = p.out_planes == 2;
+        uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) hi[j] = umma::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        for (int j = 0; j < 8; ++j) umma::pack_split2(v[2 * j], v[2 * j + 1], split, hi[j], lo[j]);
         uint4* dst = (uint4*)o;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-        if (p.out_planes == 2) {
-          uint32_t lo[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float h0 = __uint_as_float(hi[j] << 16), h1 = __uint_as_float(hi[j] & 0xffff0000u);
-            lo[j] = umma::pack_bf16x2(v[2 * j] - h0, v[2 * j + 1] - h1);
-          }
+        dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        if (split) {
           uint4* dst2 = (uint4*)(o + p.out_plane_stride);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dst2[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          dst2[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          dst2[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
       }
     }
@@ -240,15 +301,24 @@ k_upsample2x(const __nv_bfloat16* __restrict__ in, int in_planes, long long in_p
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
         const long long off = ((long long)ys[a] * w + xs[b]) * c + cc;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) val[a * 2 + b][k] = 0.f;
-        for (int pl = 0; pl < in_planes; ++pl) {
-          const uint4 u = *(const uint4*)(in + pl * in_plane_stride + off);
+        {
+          const uint4 u = *(const uint4*)(in + off);
           const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            val[a * 2 + b][2 * k] += __uint_as_float(uu[k] << 16);
-            val[a * 2 + b][2 * k + 1] += __uint_as_float(uu[k] & 0xffff0000u);
+            const float2 f = umma::unpack_plane0(uu[k], in_planes == 2);
+            val[a * 2 + b][2 * k] = f.x;
+            val[a * 2 + b][2 * k + 1] = f.y;
+          }
+        }
+        if (in_planes == 2) {
+          const uint4 u = *(const uint4*)(in + in_plane_stride + off);
+          const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&uu[k]));
+            val[a * 2 + b][2 * k] += f.x;
+            val[a * 2 + b][2 * k + 1] += f.y;
           }
         }
       }
@@ -257,18 +327,11 @@ k_upsample2x(const __nv_bfloat16* __restrict__ in, int in_planes, long long in_p
     for (int k = 0; k < 8; ++k)
       acc[k] = wy[0] * (wx[0] * val[0][k] + wx[1] * val[1][k]) + wy[1] * (wx[0] * val[2][k] + wx[1] * val[3][k]);
     __nv_bfloat16* o = out + pix * Cout_total + cout_off + cc;
-    uint32_t hi[4];
+    uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) hi[k] = umma::pack_bf16x2(acc[2 * k], acc[2 * k + 1]);
+    for (int k = 0; k < 4; ++k) umma::pack_split2(acc[2 * k], acc[2 * k + 1], out_planes == 2, hi[k], lo[k]);
     *(uint4*)o = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    if (out_planes == 2) {
-      uint32_t lo[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        lo[k] = umma::pack_bf16x2(acc[2 * k] - __uint_as_float(hi[k] << 16),
-                                  acc[2 * k + 1] - __uint_as_float(hi[k] & 0xffff0000u));
-      *(uint4*)(o + out_plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
+    if (out_planes == 2) *(uint4*)(o + out_plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -303,6 +366,14 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
 }  // namespace himo
 
 using namespace himo;
+
+static int g_flush_iters = 8;
+// Tuning knob (process-wide): length of one TMEM accumulation chain in k-iterations of 32 channels.
+extern "C" int himo_conv_set_flush_iters(int iters) {
+  if (iters < 1) return HIMO_ERR_ARG;
+  g_flush_iters = iters;
+  return HIMO_OK;
+}
 
 extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
   if (!d || !d->in || !d->wgt || !d->out) return HIMO_ERR_ARG;
@@ -366,11 +437,13 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
   p.bias = d->bias; p.out = d->out; p.out_planes = d->out_planes; p.out_plane_stride = d->out_plane_stride;
   p.W_out = W_out; p.Cout_total = d->Cout_total; p.cout_off = d->cout_off;
   p.cout_group_stride = d->cout_group_stride; p.act = d->act; p.out_fp32 = d->out_fp32;
+  p.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
+  p.flush_iters = g_flush_iters;   // k-iterations (2 hi*hi MMAs each) per TMEM accumulation chain
   const int n_ctas = p.tiles_x * p.tiles_y * p.n_tiles_n * groups;
 #define HIMO_CONV_CASE(bn, pp, st) \
   if (BN == bn && P == pp) return launch_conv<bn, BK, pp, st>(tmA, tmB, p, n_ctas, stream);
-  HIMO_CONV_CASE(128, 2, 3)
-  HIMO_CONV_CASE(96, 2, 3)
+  HIMO_CONV_CASE(128, 2, 6)
+  HIMO_CONV_CASE(96, 2, 7)
   HIMO_CONV_CASE(64, 2, 4)
   HIMO_CONV_CASE(128, 1, 6)
   HIMO_CONV_CASE(96, 1, 6)

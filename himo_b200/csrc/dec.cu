@@ -1,0 +1,194 @@
+// himo_b200/csrc/dec.cu -- H4 back end: the per-point ConvGRU flow decoder of SeFlow++.
+//
+// Replaces ConvGRUDecoder.forward_single + ConvGRU.forward (OSF/src/models/basic/decoder.py:177-237).
+// The three Conv1d(288->192, k=1) of the GRU and Linear(288->48) are GEMMs over the points; they run
+// on the same tcgen05 kernel as the backbone (csrc/conv.cu, the points viewed as a [N/128,128] image,
+// 1x1 taps) with sigmoid / tanh / GELU fused into the TMEM epilogue.  This file holds the memory-bound
+// glue around them: the gather of the 2x96 pillar vectors + offset encoder, r*h, the state update and
+// the final Linear(48->3).  Points are NOT compacted: dropped points (key < 0) ride along as zero rows
+// so that no size ever has to come back to the host.
+#include "common.cuh"
+#include "dec.cuh"
+#include "himo_b200.h"
+#include "umma.cuh"
+
+namespace himo {
+
+
+using umma::store_split;
+
+// one warp per point; lanes sweep the 288 channels of [before(96) | after(96) | offset feature(96)]
+__global__ void __launch_bounds__(256)
+k_dec_gather(DecGatherArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < a.n_pad; i += gridDim.x * wpb) {
+    float4 p = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    if (i < a.n) p = a.pt4[i];
+    const int key = __float_as_int(p.w);
+    float* h = a.h32 + (size_t)i * 192;
+    __nv_bfloat16* hx = a.hx_planes + (size_t)i * 288;
+    __nv_bfloat16* rhx = a.rhx_planes + (size_t)i * 288;
+    if (key < 0) {
+      for (int c = lane; c < 192; c += 32) h[c] = 0.f;
+      for (int c = lane; c < 288; c += 32) {
+        store_split(hx + c, a.plane_stride, a.planes, 0.f);
+        if (c >= 192) store_split(rhx + c, a.plane_stride, a.planes, 0.f);
+      }
+      continue;
+    }
+    // before_pseudoimage[:, y, x]: the (exact fp32) voxel feature of each frame, zero where empty
+    for (int f = 0; f < a.n_frames; ++f) {
+      const unsigned* bm = a.bitmap + (size_t)f * a.n_words;
+      float v = 0.f;
+      if ((__ldg(bm + (key >> 5)) >> (key & 31)) & 1u) {
+        const int r = bitmap_rank_lb(bm, a.word_prefix + (size_t)f * a.n_words, key);
+        v = __ldg(a.voxel_feats + ((size_t)f * a.n_max + r) * 32 + lane);
+      }
+      h[f * 32 + lane] = v;
+      store_split(hx + f * 32 + lane, a.plane_stride, a.planes, v);
+    }
+    // after_pseudoimage[:, y, x]
+    const float* av = a.after + (size_t)key * a.c_after;
+    for (int c = lane; c < 96; c += 32) {
+      const float v = __ldg(av + c);
+      h[96 + c] = v;
+      store_split(hx + 96 + c, a.plane_stride, a.planes, v);
+    }
+    // point_offsets = p - ((c * voxel_size + min) + voxel_size/2), every step rounded to fp32
+    // (DynamicVoxelizer._get_point_offsets, encoder.py:506-523)
+    const int cy = key / a.gx, cx = key - cy * a.gx;
+    const float ox = p.x - __fadd_rn(__fadd_rn(__fmul_rn((float)cx, a.vx), a.x_min), a.hx);
+    const float oy = p.y - __fadd_rn(__fadd_rn(__fmul_rn((float)cy, a.vy), a.y_min), a.hy);
+    const float oz = p.z - __fadd_rn(__fadd_rn(__fmul_rn(0.f, a.vz), a.z_min), a.hz);
+    for (int c = lane; c < 96; c += 32) {
+      float v = __ldg(a.w_off + c * 3) * ox;
+      v = fmaf(__ldg(a.w_off + c * 3 + 1), oy, v);
+      v = fmaf(__ldg(a.w_off + c * 3 + 2), oz, v);
+      v += __ldg(a.b_off + c);
+      store_split(hx + 192 + c, a.plane_stride, a.planes, v);
+      store_split(rhx + 192 + c, a.plane_stride, a.planes, v);
+    }
+  }
+}
+
+// rhx[:, :192] = split(r * h)      (ConvGRU.forward: rh_x = cat([r*h, x]), decoder.py:189)
+__global__ void __launch_bounds__(256)
+k_dec_rh(const float* __restrict__ zr, const float* __restrict__ h32, int n_pad,
+         __nv_bfloat16* __restrict__ rhx, int planes, long long plane_stride) {
+  const long long total = (long long)n_pad * 192;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / 192;
+    const int c = (int)(t - i * 192);
+    const float r = zr[i * 384 + 192 + c];
+    store_split(rhx + i * 288 + c, plane_stride, planes, r * h32[t]);
+  }
+}
+
+// h = (1 - z) * h + z * q          (decoder.py:192)
+__global__ void __launch_bounds__(256)
+k_dec_update(const float* __restrict__ zr, const float* __restrict__ q, float* __restrict__ h32, int n_pad,
+             __nv_bfloat16* __restrict__ hx, int planes, long long plane_stride) {
+  const long long total = (long long)n_pad * 192;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / 192;
+    const int c = (int)(t - i * 192);
+    const float z = zr[i * 384 + c];
+    const float hn = __fadd_rn(__fmul_rn(1.0f - z, h32[t]), __fmul_rn(z, q[t]));
+    h32[t] = hn;
+    store_split(hx + i * 288 + c, plane_stride, planes, hn);
+  }
+}
+
+// flow = Linear(48->3)(y); y already holds GELU(Linear(288->48)) from the GEMM epilogue.
+__global__ void __launch_bounds__(256)
+k_dec_out(const float* __restrict__ y, int y_stride, const float4* __restrict__ pt4, int n,
+          const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ flow) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float o[3] = {0.f, 0.f, 0.f};
+    if (__float_as_int(pt4[i].w) >= 0) {
+      const float4* yr = (const float4*)(y + (size_t)i * y_stride);
+      float yv[48];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        float4 t = yr[k];
+        yv[4 * k] = t.x; yv[4 * k + 1] = t.y; yv[4 * k + 2] = t.z; yv[4 * k + 3] = t.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float acc = __ldg(w2 + j * 48) * yv[0];
+#pragma unroll
+        for (int k = 1; k < 48; ++k) acc = fmaf(__ldg(w2 + j * 48 + k), yv[k], acc);
+        o[j] = acc + __ldg(b2 + j);
+      }
+    }
+    flow[3 * (size_t)i] = o[0]; flow[3 * (size_t)i + 1] = o[1]; flow[3 * (size_t)i + 2] = o[2];
+  }
+}
+
+// pose_flow + flow assembly and ordered compaction helpers -------------------------------------
+__global__ void __launch_bounds__(256)
+k_valid_flags_write(const float4* __restrict__ pt4, int n, const int* __restrict__ pos,
+                    int64_t* __restrict__ valid_idx, const float* __restrict__ flow_all,
+                    float* __restrict__ flow_valid) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (__float_as_int(pt4[i].w) >= 0) {
+      const int j = pos[i];
+      valid_idx[j] = i;
+      flow_valid[3 * (size_t)j] = flow_all[3 * (size_t)i];
+      flow_valid[3 * (size_t)j + 1] = flow_all[3 * (size_t)i + 1];
+      flow_valid[3 * (size_t)j + 2] = flow_all[3 * (size_t)i + 2];
+    }
+  }
+}
+
+struct MapValidPt4 {
+  const float4* p;
+  __device__ int operator()(int i) const { return __float_as_int(p[i].w) >= 0 ? 1 : 0; }
+};
+
+}  // namespace himo
+
+using namespace himo;
+
+// C++-level entry points used by deflowpp.cu (same shared object).
+namespace himo {
+
+int dec_gather(const DecGatherArgs& a, cudaStream_t stream) {
+  k_dec_gather<<<min(ceil_div(a.n_pad, 8), kNumSMs * 8), 256, 0, stream>>>(a);
+  HIMO_LAUNCH_RET();
+  return HIMO_OK;
+}
+int dec_rh(const float* zr, const float* h32, int n_pad, __nv_bfloat16* rhx, int planes, long long ps,
+           cudaStream_t stream) {
+  k_dec_rh<<<kNumSMs * 8, 256, 0, stream>>>(zr, h32, n_pad, rhx, planes, ps);
+  HIMO_LAUNCH_RET();
+  return HIMO_OK;
+}
+int dec_update(const float* zr, const float* q, float* h32, int n_pad, __nv_bfloat16* hx, int planes,
+               long long ps, cudaStream_t stream) {
+  k_dec_update<<<kNumSMs * 8, 256, 0, stream>>>(zr, q, h32, n_pad, hx, planes, ps);
+  HIMO_LAUNCH_RET();
+  return HIMO_OK;
+}
+int dec_out(const float* y, int y_stride, const float4* pt4, int n, const float* w2, const float* b2,
+            float* flow, cudaStream_t stream) {
+  if (n <= 0) return HIMO_OK;
+  k_dec_out<<<min(ceil_div(n, 256), kNumSMs * 8), 256, 0, stream>>>(y, y_stride, pt4, n, w2, b2, flow);
+  HIMO_LAUNCH_RET();
+  return HIMO_OK;
+}
+// ordered compaction of the valid points: valid_idx [n_valid] i64, flow_valid [n_valid,3], n_valid (device)
+int dec_compact(const float4* pt4, int n, int* pos, int* n_valid, void* scan_scratch, int64_t* valid_idx,
+                const float* flow_all, float* flow_valid, cudaStream_t stream) {
+  HIMO_CUDA_RET(scan_exclusive(MapValidPt4{pt4}, pos, n, nullptr, n_valid, scan_scratch, stream));
+  if (n <= 0) return HIMO_OK;
+  k_valid_flags_write<<<min(ceil_div(n, 256), kNumSMs * 8), 256, 0, stream>>>(pt4, n, pos, valid_idx, flow_all,
+                                                                             flow_valid);
+  HIMO_LAUNCH_RET();
+  return HIMO_OK;
+}
+
+}  // namespace himo

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -124,6 +125,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -146,14 +157,48 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t smem_addr) {
   d |= layout << 61;
   return d;
 }
-// Instruction descriptor for kind::f16: A,B = bf16 (K-major), D = fp32, M x N tile.
-__host__ __device__ constexpr uint32_t idesc_bf16_f32(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// Instruction descriptor for kind::f16: A,B 16-bit K-major (format 0 = fp16, 1 = bf16, chosen
+// independently for A and B), D = fp32, M x N tile.
+__host__ __device__ constexpr uint32_t idesc_f16kind_f32(int m, int n, uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t idesc_bf16_f32(int m, int n) { return idesc_f16kind_f32(m, n, 1, 1); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// Split-plane element formats.  planes == 1: plane 0 = bf16(v) (plain bf16 GEMM operand).
+// planes == 2: plane 0 = fp16(v), plane 1 = fp16(v - plane0): 11 + 11 mantissa bits, fp32-class.
+__device__ __forceinline__ void store_split(__nv_bfloat16* dst, long long plane_stride, int planes, float v) {
+  if (planes == 2) {
+    const __half hi = __float2half_rn(v);
+    reinterpret_cast<__half*>(dst)[0] = hi;
+    reinterpret_cast<__half*>(dst)[plane_stride] = __float2half_rn(v - __half2float(hi));
+  } else {
+    dst[0] = __float2bfloat16_rn(v);
+  }
+}
+// two consecutive channels -> packed 16-bit pairs for plane 0 (and plane 1 when split)
+__device__ __forceinline__ void pack_split2(float a, float b, bool split, uint32_t& hi, uint32_t& lo) {
+  if (split) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = pack_f16x2(a - hf.x, b - hf.y);
+  } else {
+    hi = pack_bf16x2(a, b);
+    lo = 0u;
+  }
+}
+__device__ __forceinline__ float2 unpack_plane0(uint32_t u, bool split) {
+  if (split) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
 }  // namespace umma

@@ -39,12 +39,14 @@ def _bn(rng, c, prefix, sd):
     sd[prefix + ".num_batches_tracked"] = torch.tensor(1, dtype=torch.long)
 
 
-def synth_deflowpp_state_dict(seed: int = 0, act_gain: float = 1.5) -> Dict[str, torch.Tensor]:
+def synth_deflowpp_state_dict(seed: int = 0, act_gain: float = 1.5, dec_gain: float = 0.6,
+                              flow_gain: float = 0.12) -> Dict[str, torch.Tensor]:
     """Seeded DeFlowPP weights with the 156 state_dict entries of the reference class
     (OSF/src/models/deflow.py:90-113).  Xavier-uniform weights (the reference's weights_init,
     OSF/src/utils/mics.py:98-105) with a gain on the GELU layers that keeps activations O(1) through
     the 16-layer encoder, small non-zero biases and non-trivial BatchNorm running statistics so
-    that BN folding is really exercised."""
+    that BN folding is really exercised.  dec_gain / flow_gain keep the backbone output O(1-10) and
+    the predicted flow in the physical range of a 10 Hz sweep pair (|flow| up to a few metres)."""
     rng = np.random.default_rng(seed)
     sd: Dict[str, torch.Tensor] = {}
     p = "embedder.feature_net.pfn_layers.0"
@@ -59,7 +61,7 @@ def synth_deflowpp_state_dict(seed: int = 0, act_gain: float = 1.5) -> Dict[str,
         q = "backbone." + name
         for sub, shape in ((".u1_u2.0", (latent, skip, 1, 1)), (".u3", (latent, latent, 1, 1)),
                            (".u4_u5.0", (out, 2 * latent, 3, 3)), (".u4_u5.1", (out, out, 3, 3))):
-            sd[q + sub + ".weight"] = _xavier(rng, shape, 1.0)
+            sd[q + sub + ".weight"] = _xavier(rng, shape, dec_gain if sub.startswith(".u4") else 1.0)
             sd[q + sub + ".bias"] = torch.from_numpy(rng.uniform(-0.05, 0.05, shape[0]).astype(np.float32))
     sd["backbone.decoder_step4.weight"] = _xavier(rng, (96, 96, 3, 3), 1.0)
     sd["backbone.decoder_step4.bias"] = torch.from_numpy(rng.uniform(-0.05, 0.05, 96).astype(np.float32))
@@ -70,7 +72,7 @@ def synth_deflowpp_state_dict(seed: int = 0, act_gain: float = 1.5) -> Dict[str,
         sd[f"head.gru.{g}.bias"] = torch.from_numpy(rng.uniform(-0.05, 0.05, 192).astype(np.float32))
     sd["head.decoder.0.weight"] = _xavier(rng, (48, 288), 1.0)
     sd["head.decoder.0.bias"] = torch.from_numpy(rng.uniform(-0.05, 0.05, 48).astype(np.float32))
-    sd["head.decoder.2.weight"] = _xavier(rng, (3, 48), 1.0)
+    sd["head.decoder.2.weight"] = _xavier(rng, (3, 48), flow_gain)
     sd["head.decoder.2.bias"] = torch.from_numpy(rng.uniform(-0.05, 0.05, 3).astype(np.float32))
     return sd
 

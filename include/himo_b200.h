@@ -94,15 +94,18 @@ int himo_chamfer_backward(const float* pc0, int n0, const float* pc1, int n1, co
  *           ConvWithNorms.forward (OSF/src/models/basic/__init__.py:76-94) and
  *           UpsampleSkip.forward / decoder_step4 (OSF/src/models/basic/unet.py:18-35,130),
  *           i.e. every layer of UNetThreeFrame.forward (unet.py:131-166).
- * Activations are NHWC bf16 "planes": plane 0 = bf16(x), optional plane 1 = bf16(x - plane0)
- * (split-bf16; two planes give fp32-class products on the bf16 tensor cores).
+ * Activations are NHWC 16-bit "planes".  in_planes == 2: split fp16, plane 0 = fp16(x),
+ * plane 1 = fp16(x - plane0) (fp32-class products from three tensor-core MMAs per k-step);
+ * in_planes == 1: plain bf16.  Weights follow the same format; in split mode the host pre-scales
+ * them by a power of two and passes its inverse as acc_scale (applied to the accumulator before
+ * the bias), so their low plane stays in fp16's normal range.
  *   in      [in_planes][H_in][W_in][Cin_total] bf16; the conv reads channels
  *           [cin_off + g*cin_group_stride, +Cin) for group g (groups = frames sharing weights)
  *   wgt     [in_planes][Cout][ksize*ksize*Cin] bf16, K index = (ky*ksize + kx)*Cin + ci
  *   bias    [Cout] f32 or NULL (BatchNorm folded in by the host)
  *   out     NHWC, channels [cout_off + g*cout_group_stride, +Cout) of Cout_total; bf16 planes
  *           (out_planes 1|2) or fp32 (out_fp32 = 1)
- *   ksize 1|3 (padding ksize/2), stride 1|2, act 0 none | 1 exact-erf GELU
+ *   ksize 1|3 (padding ksize/2), stride 1|2, act 0 none | 1 exact-erf GELU | 2 sigmoid | 3 tanh
  */
 typedef struct himo_conv_desc {
   const void* in;
@@ -118,14 +121,118 @@ typedef struct himo_conv_desc {
   int Cout_total, cout_off;
   int out_fp32, act;
   int n_groups, cin_group_stride, cout_group_stride;
+  float acc_scale;            /* accumulator multiplier before bias/activation; 0 means 1 */
 } himo_conv_desc;
 int himo_conv2d_nhwc(const himo_conv_desc* desc, void* stream);
+/* Split-mode accuracy/speed knob: k-iterations (32 input channels each) accumulated in tensor memory
+ * before the partial sum is drained into fp32 registers (default 8).  Process-wide. */
+int himo_conv_set_flush_iters(int iters);
 /* replaces: F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) of
  *           BilinearDecoder.forward (OSF/src/models/basic/unet.py:7-16); in [h][w][c] planes ->
  *           channels [cout_off, +c) of out [2h][2w][Cout_total] planes. */
 int himo_upsample2x_nhwc(const void* in, int in_planes, long long in_plane_stride, int h, int w, int c,
                          void* out, int out_planes, long long out_plane_stride, int Cout_total,
                          int cout_off, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * H1+H4  fused point embedder for the frames of one tuple (SeFlow++: t-1, t, t+1)
+ * replaces: DynamicEmbedder.forward (OSF/src/models/basic/encoder.py:618-631) =
+ *           DynamicVoxelizer (:567-600) + DynamicPillarFeatureNet (:430-475, two DynamicScatter
+ *           calls) + PointPillarsScatter (:126-147), preceded by the rigid warp of
+ *           wrap_batch_pcs (OSF/src/models/basic/__init__.py:50,57), for every frame.
+ * points[f]    [num_points[f],3] f32 (ground-free; NaN rows = padding, dropped)
+ * transform[f] row-major 3x4 (R|t) applied as p @ R^T + t when has_transform[f]
+ * pfn_weight   [32,9] f32 and pfn_bias [32] f32: Linear(9,32,bias=False) with BatchNorm1d folded
+ * canvas       [canvas_planes][gy][gx][n_frames*32] bf16 (split-bf16 planes); frame f owns
+ *              channels [32f, 32f+32).  Cleared here unless skip_canvas_clear.
+ * All per-point / per-voxel results stay in `workspace` (see himo_embed_views).
+ */
+#define HIMO_MAX_FRAMES 4
+typedef struct himo_embed_desc {
+  int n_frames;
+  int n_max;                       /* row capacity of the per-frame workspace arrays */
+  const float* points[HIMO_MAX_FRAMES];
+  int num_points[HIMO_MAX_FRAMES];
+  int has_transform[HIMO_MAX_FRAMES];
+  float transform[HIMO_MAX_FRAMES][12];
+  float voxel_size[3];
+  float coors_range[6];
+  double voxel_size_f64[3];        /* the Python-side doubles behind x_offset = vx/2 + x_min */
+  double coors_range_f64[6];
+  const float* pfn_weight;
+  const float* pfn_bias;
+  void* canvas;
+  int canvas_planes;
+  int skip_canvas_clear;
+  void* workspace;
+  size_t workspace_bytes;
+} himo_embed_desc;
+typedef struct himo_embed_view {     /* device pointers into the embed workspace, rows = frames */
+  float* pt4;            /* [F][n_max][4] warped xyz + int32 cell key (y*gx+x, -1 = dropped) */
+  unsigned* bitmap;      /* [F][n_words] occupancy bits */
+  int* word_prefix;      /* [F][n_words] exclusive popcount prefix (voxel rank base) */
+  int* num_voxels;       /* [F] */
+  int* rank;             /* [F][n_max] point -> voxel (sorted order), -1 = dropped: point2voxel */
+  int* voxel_count;      /* [F][n_max+1] */
+  int* seg_start;        /* [F][n_max+1] */
+  int* sorted_idx;       /* [F][n_max] */
+  float* voxel_feats;    /* [F][n_max][32] */
+  float* voxel_mean;     /* [F][n_max][3] */
+  int* voxel_key;        /* [F][n_max] */
+  int n_words;
+} himo_embed_view;
+size_t himo_embed_workspace_bytes(int n_frames, int n_max, const float* voxel_size,
+                                  const float* coors_range);
+int himo_embed_frames(const himo_embed_desc* desc, void* stream);
+int himo_embed_views(int n_frames, int n_max, const float* voxel_size, const float* coors_range,
+                     void* workspace, himo_embed_view* out);
+
+/* ------------------------------------------------------------------------------------------
+ * H4  SeFlow++ network forward for one frame triple
+ * replaces: DeFlowPP.forward (OSF/src/models/deflow.py:115-158) behind the model-level boundary
+ *           `model(batch) -> {"flow", "pose_flow", "pc0_valid_point_idxes", ...}` that
+ *           ModelWrapper.test_step drives (OSF/src/trainer.py:290-343).
+ * Weights are packed by the host (himo_b200/deflowpp.py): BatchNorm folded, conv weights as
+ * [planes][Cout][taps*Cin] bf16 split planes (see himo_conv_desc).
+ */
+typedef struct himo_deflowpp_weights {
+  int planes;                               /* 1 = bf16, 2 = split-bf16 (fp32-class) */
+  const float* pfn_w; const float* pfn_b;   /* [32,9], [32] */
+  const void* enc_w[16]; const float* enc_b[16];        /* encoder_step_1..3 in order */
+  const void* dec_w[3][4]; const float* dec_b[3][4];    /* decoder_step1..3: u1, u3, u4, u5 */
+  const void* dec4_w; const float* dec4_b;
+  const float* off_w; const float* off_b;               /* head.offset_encoder [96,3],[96] */
+  const void* gru_zr_w; const float* gru_zr_b;          /* [planes][384][288] = [convz; convr], [384] */
+  const void* gru_q_w; const float* gru_q_b;            /* [planes][192][288], [192] */
+  const void* dec0_w; const float* dec0_b;              /* head.decoder.0 padded to 64 rows */
+  const float* dec2_w; const float* dec2_b;             /* head.decoder.2 [3,48],[3] */
+  /* accumulator scales (inverse of the power-of-two weight pre-scale) per GEMM, 0 = 1 */
+  float enc_s[16]; float dec_s[3][4]; float dec4_s; float gru_zr_s; float gru_q_s; float dec0_s;
+} himo_deflowpp_weights;
+typedef struct himo_deflowpp_io {
+  const float* pch1; int n_h1;              /* t-1 cloud, ground-free, sensor frame */
+  const float* pc0; int n0;
+  const float* pc1; int n1;
+  float T_h1[12]; float T_0[12];            /* (R|t) of inv(pose1)@poseh1 and inv(pose1)@pose0, fp32 */
+  int n_max;                                /* workspace row capacity (>= every n) */
+  int num_iters;                            /* GRU iterations (2 for SeFlow++) */
+  float* flow_all;                          /* [n0,3] network flow per pc0 point, 0 where dropped */
+  int64_t* valid_idx;                       /* optional [n0]: pc0_valid_point_idxes (first n_valid) */
+  float* flow_valid;                        /* optional [n0,3]: flow in the reference's compact form */
+  int32_t* n_valid;                         /* optional DEVICE int32[1] */
+  void* workspace; size_t workspace_bytes;
+} himo_deflowpp_io;
+typedef struct himo_deflowpp_view {
+  void* canvas; void* Fstar; void* Lstar; void* Rstar; void* S; void* T; void* U; float* V;
+  void* embed_ws; float* h32;
+} himo_deflowpp_view;
+size_t himo_deflowpp_workspace_bytes(int n_max, int planes);
+int himo_deflowpp_forward(const himo_deflowpp_weights* w, const himo_deflowpp_io* io, void* stream);
+int himo_deflowpp_views(int n_max, int planes, void* workspace, himo_deflowpp_view* out);
+/* out[i] = (p_i @ R^T + t) - p_i (+ add_flow[i] if given): pose flow / final-flow assembly of
+ * ModelWrapper.test_step (OSF/src/trainer.py:320-335).  T12_dev: DEVICE float[12]. */
+int himo_rigid_flow(const float* points, int n, const float* T12_dev, const float* add_flow, float* out,
+                    void* stream);
 
 #ifdef __cplusplus
 }
