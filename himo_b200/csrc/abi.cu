@@ -15,3 +15,8 @@ extern "C" const char* himo_status_string(int status) {
   if (status > 0) return cudaGetErrorString((cudaError_t)status);
   return "unknown himo status";
 }
+
+#include <atomic>
+static std::atomic<unsigned long long> g_launches{0};
+extern "C" void himo_count_launch_(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" unsigned long long himo_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

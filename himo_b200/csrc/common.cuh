@@ -15,8 +15,12 @@
     cudaError_t _e = (expr);                        \
     if (_e != cudaSuccess) return (int)_e;          \
   } while (0)
+// Every kernel launch in this library is followed by HIMO_LAUNCH_RET(): it also bumps the
+// process-wide launch counter that bench.py reports as "gpu_launches" (diagnostic only).
+extern "C" void himo_count_launch_(void);
 #define HIMO_LAUNCH_RET()                           \
   do {                                              \
+    himo_count_launch_();                           \
     cudaError_t _e = cudaGetLastError();            \
     if (_e != cudaSuccess) return (int)_e;          \
   } while (0)
@@ -178,6 +182,7 @@ inline cudaError_t scan_exclusive(MapFn map, int* out, int n_max, const int* n_d
   int* counter = (int*)(status + tiles + 1);
   k_scan_lookback<<<(unsigned)tiles, kScanThreads, 0, stream>>>(map, out, n_max, n_dev, status, counter,
                                                                 total_out);
+  himo_count_launch_();
   return cudaGetLastError();
 }
 

@@ -95,6 +95,10 @@ extern "C" int himo_deflowpp_forward(const himo_deflowpp_weights* w, const himo_
   NetBuffers nb;
   if (net_layout(io->n_max, P, vs, cr, &nb, io->workspace) > io->workspace_bytes) return HIMO_ERR_WORKSPACE;
 
+  auto mark = [&](int k) {
+    if (io->stage_events[k]) cudaEventRecord((cudaEvent_t)io->stage_events[k], stream);
+  };
+  mark(0);
   // ---- embedder x3 (deflow.py:129-131); frame order (pch1, pc0, pc1) = channel slices 0,1,2
   himo_embed_desc e;
   e.n_frames = 3; e.n_max = io->n_max;
@@ -112,6 +116,7 @@ extern "C" int himo_deflowpp_forward(const himo_deflowpp_weights* w, const himo_
   e.workspace = nb.embed_ws; e.workspace_bytes = nb.embed_ws_bytes;
   HIMO_RET(himo_embed_frames(&e, stream));
 
+  mark(1);
   // ---- shared encoder on the three pseudo-images (unet.py:139-150), frames = conv groups
   int li = 0;
   auto enc = [&](const Act& in, int cin, const Act& out, int cout, int stride) {
@@ -144,6 +149,7 @@ extern "C" int himo_deflowpp_forward(const himo_deflowpp_weights* w, const himo_
   HIMO_RET(up_block(2, nb.Tt, nb.B, 96, 96, nb.T3, nb.CAT3, nb.X3, nb.U));
   HIMO_RET(conv(nb.U, 0, 96, 1, w->dec4_w, w->dec4_b, 96, 3, 1, 0, nb.U, 0, P, stream, w->dec4_s, nb.V));
 
+  mark(2);
   // ---- ConvGRU decoder on the pc0 points (decoder.py:210-237)
   const int n0 = io->n0;
   if (n0 > 0) {
@@ -176,6 +182,7 @@ extern "C" int himo_deflowpp_forward(const himo_deflowpp_weights* w, const himo_
   } else if (io->n_valid) {
     HIMO_CUDA_RET(cudaMemsetAsync(io->n_valid, 0, sizeof(int), stream));
   }
+  mark(3);
   return HIMO_OK;
 }
 
@@ -196,7 +203,7 @@ extern "C" int himo_deflowpp_views(int n_max, int planes, void* workspace, himo_
 namespace himo {
 __global__ void __launch_bounds__(256)
 k_rigid_flow(const float* __restrict__ pts, int n, const float* __restrict__ T12, float* __restrict__ out,
-             const float* __restrict__ add, const uint8_t* __restrict__ ground_mask) {
+             const float* __restrict__ add, const int32_t* __restrict__ src) {
   float T[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) T[k] = T12[k];
@@ -205,8 +212,9 @@ k_rigid_flow(const float* __restrict__ pts, int n, const float* __restrict__ T12
     float fx = __fadd_rn(__fmaf_rn(z, T[2], __fmaf_rn(y, T[1], __fmul_rn(x, T[0]))), T[3]) - x;
     float fy = __fadd_rn(__fmaf_rn(z, T[6], __fmaf_rn(y, T[5], __fmul_rn(x, T[4]))), T[7]) - y;
     float fz = __fadd_rn(__fmaf_rn(z, T[10], __fmaf_rn(y, T[9], __fmul_rn(x, T[8]))), T[11]) - z;
-    if (add && !(ground_mask && ground_mask[i])) {
-      fx += add[3 * (size_t)i]; fy += add[3 * (size_t)i + 1]; fz += add[3 * (size_t)i + 2];
+    if (add) {
+      const int j = src ? src[i] : i;
+      if (j >= 0) { fx += add[3 * (size_t)j]; fy += add[3 * (size_t)j + 1]; fz += add[3 * (size_t)j + 2]; }
     }
     out[3 * (size_t)i] = fx; out[3 * (size_t)i + 1] = fy; out[3 * (size_t)i + 2] = fz;
   }
@@ -220,6 +228,17 @@ extern "C" int himo_rigid_flow(const float* points, int n, const float* T12_dev,
   if (!points || !T12_dev || !out) return HIMO_ERR_ARG;
   k_rigid_flow<<<min(ceil_div(n, 256), kNumSMs * 8), 256, 0, (cudaStream_t)stream_>>>(points, n, T12_dev, out,
                                                                                      add_flow, nullptr);
+  HIMO_LAUNCH_RET();
+  return HIMO_OK;
+}
+
+extern "C" int himo_final_flow(const float* points_all, int n_all, const float* T12_dev, const float* flow,
+                               const int32_t* src_index, float* out, void* stream_) {
+  if (n_all < 0) return HIMO_ERR_ARG;
+  if (n_all == 0) return HIMO_OK;
+  if (!points_all || !T12_dev || !out) return HIMO_ERR_ARG;
+  k_rigid_flow<<<min(ceil_div(n_all, 256), kNumSMs * 8), 256, 0, (cudaStream_t)stream_>>>(points_all, n_all, T12_dev,
+                                                                                         out, flow, src_index);
   HIMO_LAUNCH_RET();
   return HIMO_OK;
 }

@@ -45,6 +45,7 @@ class _IO(ctypes.Structure):
         ("n_max", c_int), ("num_iters", c_int),
         ("flow_all", c_void_p), ("valid_idx", c_void_p), ("flow_valid", c_void_p), ("n_valid", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("stage_events", c_void_p * 4),
     ]
 
 
@@ -57,6 +58,8 @@ _lib.register("himo_deflowpp_workspace_bytes", c_size_t, [c_int, c_int])
 _lib.register("himo_deflowpp_forward", c_int, [ctypes.POINTER(_Weights), ctypes.POINTER(_IO), c_void_p])
 _lib.register("himo_deflowpp_views", c_int, [c_int, c_int, c_void_p, ctypes.POINTER(_View)])
 _lib.register("himo_rigid_flow", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p])
+_lib.register("himo_final_flow", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p])
+_lib.register("himo_launch_count", ctypes.c_ulonglong, [])
 
 
 def cal_pose0to1(pose0: torch.Tensor, pose1: torch.Tensor) -> torch.Tensor:
@@ -192,7 +195,8 @@ class DeFlowPP:
         return self._ws
 
     def forward_triple(self, pch1: torch.Tensor, pc0: torch.Tensor, pc1: torch.Tensor,
-                       T_h1: torch.Tensor, T_0: torch.Tensor, compact: bool = True) -> Dict[str, torch.Tensor]:
+                       T_h1: torch.Tensor, T_0: torch.Tensor, compact: bool = True,
+                       stage_events=None) -> Dict[str, torch.Tensor]:
         """One frame triple.  pch1/pc0/pc1: [N,3] f32 CUDA (ground-free, sensor frames);
         T_h1/T_0: [4,4] f32 host transforms into the pc1 frame (cal_pose0to1).
         Returns flow_all [N0,3] (0 where the point was dropped) and, if compact, the reference's
@@ -230,6 +234,9 @@ class DeFlowPP:
                 out.update(valid_idx=valid_idx, flow_valid=flow_valid, n_valid=n_valid)
             io.workspace = ws.data_ptr()
             io.workspace_bytes = ws.numel()
+            if stage_events is not None:            # 4 torch.cuda.Event(enable_timing=True), already created
+                for k in range(4):
+                    io.stage_events[k] = stage_events[k].cuda_event
             st = _lib.lib().himo_deflowpp_forward(ctypes.byref(self._w), ctypes.byref(io), _lib.stream_ptr(dev))
         _lib.check(st, "himo_deflowpp_forward")
         return out

@@ -25,6 +25,8 @@ extern "C" {
 
 #define HIMO_B200_ABI_VERSION 1
 int himo_abi_version(void);
+/* Number of kernels this library has launched in this process (diagnostic; bench.py "gpu_launches"). */
+unsigned long long himo_launch_count(void);
 /* Human-readable text for a status code returned by any entry point (static storage). */
 const char* himo_status_string(int status);
 
@@ -221,6 +223,9 @@ typedef struct himo_deflowpp_io {
   float* flow_valid;                        /* optional [n0,3]: flow in the reference's compact form */
   int32_t* n_valid;                         /* optional DEVICE int32[1] */
   void* workspace; size_t workspace_bytes;
+  /* optional cudaEvent_t handles recorded on `stream` at the stage boundaries: [0] start, [1] after the
+   * embedder, [2] after the backbone (UNetThreeFrame), [3] after the decoder.  NULL entries are skipped. */
+  void* stage_events[4];
 } himo_deflowpp_io;
 typedef struct himo_deflowpp_view {
   void* canvas; void* Fstar; void* Lstar; void* Rstar; void* S; void* T; void* U; float* V;
@@ -233,6 +238,11 @@ int himo_deflowpp_views(int n_max, int planes, void* workspace, himo_deflowpp_vi
  * ModelWrapper.test_step (OSF/src/trainer.py:320-335).  T12_dev: DEVICE float[12]. */
 int himo_rigid_flow(const float* points, int n, const float* T12_dev, const float* add_flow, float* out,
                     void* stream);
+/* Total flow of ALL points of pc0 (ground included), the array ModelWrapper.test_step writes to the
+ * .h5 (OSF/src/trainer.py:320-343): out[i] = pose_flow(points_all[i]) + (src[i] >= 0 ? flow[src[i]] : 0),
+ * src = index of point i in the ground-free cloud (NULL = identity). */
+int himo_final_flow(const float* points_all, int n_all, const float* T12_dev, const float* flow,
+                    const int32_t* src_index, float* out, void* stream);
 
 #ifdef __cplusplus
 }
