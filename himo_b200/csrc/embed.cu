@@ -221,9 +221,10 @@ k_embed_pfn(EmbedArgs a, EmbedGrid g) {
     const float ccx = __fadd_rn(__fmul_rn((float)cx, g.vx), g.x_off);
     const float ccy = __fadd_rn(__fmul_rn((float)cy, g.vy), g.y_off);
     const float ccz = __fadd_rn(__fmul_rn(0.f, g.vz), g.z_off);
-    double acc = 0.0;
-    for (int k = beg; k < end; ++k) {
-      const float4 p = pt4[sorted_idx[k]];        // same address for all lanes: one broadcast load
+    // 4 points per trip with independent accumulators: the per-point chain (index -> point -> 9 FMAs ->
+    // double add) is latency-bound, and real sweeps have pillars with > 1000 points
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    auto pfn_point = [&](const float4 p) -> double {
       float y = w[0] * p.x;
       y = fmaf(w[1], p.y, y);
       y = fmaf(w[2], p.z, y);
@@ -234,8 +235,17 @@ k_embed_pfn(EmbedArgs a, EmbedGrid g) {
       y = fmaf(w[7], p.y - ccy, y);
       y = fmaf(w[8], p.z - ccz, y);
       y += b;
-      acc += (double)fmaxf(y, 0.f);
+      return (double)fmaxf(y, 0.f);
+    };
+    int k = beg;
+    for (; k + 4 <= end; k += 4) {
+      // same address for all lanes: each load is one broadcast transaction
+      const int i0 = sorted_idx[k], i1 = sorted_idx[k + 1], i2 = sorted_idx[k + 2], i3 = sorted_idx[k + 3];
+      const float4 p0 = pt4[i0], p1 = pt4[i1], p2 = pt4[i2], p3 = pt4[i3];
+      acc0 += pfn_point(p0); acc1 += pfn_point(p1); acc2 += pfn_point(p2); acc3 += pfn_point(p3);
     }
+    for (; k < end; ++k) acc0 += pfn_point(pt4[sorted_idx[k]]);
+    const double acc = (acc0 + acc1) + (acc2 + acc3);
     const float feat = __fdiv_rn((float)acc, fc);
     a.voxel_feats[((size_t)f * a.n_max + v) * 32 + lane] = feat;
     if (a.voxel_mean && lane < 3)
