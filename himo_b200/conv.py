@@ -21,6 +21,10 @@ class ConvDesc(ctypes.Structure):
         ("Cout_total", c_int), ("cout_off", c_int), ("out_fp32", c_int), ("act", c_int),
         ("n_groups", c_int), ("cin_group_stride", c_int), ("cout_group_stride", c_int),
         ("acc_scale", ctypes.c_float),
+        ("out_t", c_void_p), ("out_t_plane_stride", c_longlong), ("ld_t", c_int),
+        ("mask_src", c_void_p), ("mask_plane_stride", c_longlong), ("mask_planes", c_int),
+        ("b_group_k_stride", c_int), ("out_group_pix_stride", c_longlong), ("b_k_total", c_longlong),
+        ("stop_flag", c_void_p),
     ]
 
 

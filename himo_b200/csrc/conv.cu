@@ -45,6 +45,16 @@ struct ConvParams {
   int act, out_fp32;
   float acc_scale;
   int flush_iters;
+  // GEMM-epilogue extensions used by the FastNSF MLP (csrc/nsf.cu)
+  __nv_bfloat16* out_t;            // optional transposed copy: [planes][Cout_total][ld_t], column = pixel
+  long long out_t_plane_stride;
+  int ld_t;
+  const __nv_bfloat16* mask_src;   // optional ReLU-backward mask source, same layout as `out` (2 planes)
+  long long mask_plane_stride;
+  int mask_planes;
+  int b_group_k_stride;            // split-K: K offset of the B operand per group
+  long long out_group_pix_stride;  // split-K: output row offset per group
+  const int* stop_flag;            // optional device flag: non-zero => the whole launch is a no-op
 };
 
 __device__ __forceinline__ float gelu_erf(float v) {
@@ -92,6 +102,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   float* bias_s = (float*)(smem + S::kBarOffset + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.stop_flag && *p.stop_flag) return;   // uniform across the grid
 
   // tile decode: n-tile fastest so CTAs that share an A tile are co-scheduled (L2 reuse)
   int t = blockIdx.x;
@@ -145,7 +156,8 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             x0 * p.stride + kx - p.pad, y0 * p.stride + ky - p.pad, pl);
 #pragma unroll
         for (int pl = 0; pl < P; ++pl)
-          umma::tma_load_3d(b_dst + pl * S::kBBytes, &tmB, &full_bar[s], tap * p.Cin + kc * BK, n0, pl);
+          umma::tma_load_3d(b_dst + pl * S::kBBytes, &tmB, &full_bar[s],
+                            g * p.b_group_k_stride + tap * p.Cin + kc * BK, n0, pl);
       }
     }
   } else if (warp == 1) {
@@ -230,7 +242,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
     const int py = y0 + row / p.TW, px = x0 + row % p.TW;
-    const long long pix = (long long)py * p.W_out + px;
+    const long long pix = (long long)py * p.W_out + px + (long long)g * p.out_group_pix_stride;
     const long long ch0 = (long long)p.cout_off + (long long)g * p.cout_group_stride + n0 + half * kHalf;
 #pragma unroll
     for (int gi = 0; gi < kGroups; ++gi) {
@@ -241,7 +253,33 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         v[j] = p.act == 0 ? x
                : p.act == 1 ? gelu_erf(x)
                : p.act == 2 ? __fdiv_rn(1.0f, 1.0f + expf(-x))     // torch.sigmoid
-                            : tanhf(x);                             // torch.tanh
+               : p.act == 3 ? tanhf(x)                              // torch.tanh
+                            : fmaxf(x, 0.f);                        // ReLU
+      }
+      if (p.mask_src) {   // ReLU backward: pass the gradient where the forward activation was > 0
+        const __nv_bfloat16* m = p.mask_src + pix * p.Cout_total + ch0 + gi * 16;
+        uint32_t mb[8];
+        *(uint4*)&mb[0] = *(const uint4*)m;
+        *(uint4*)&mb[4] = *(const uint4*)(m + 8);
+        if (p.mask_planes == 2) {
+          uint32_t m2[8];
+          *(uint4*)&m2[0] = *(const uint4*)(m + p.mask_plane_stride);
+          *(uint4*)&m2[4] = *(const uint4*)(m + p.mask_plane_stride + 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mb[j] |= m2[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if ((mb[j] & 0x00007fffu) == 0u) v[2 * j] = 0.f;
+          if ((mb[j] & 0x7fff0000u) == 0u) v[2 * j + 1] = 0.f;
+        }
+      }
+      if (p.out_t) {      // transposed split-plane copy: element (channel, pixel); lanes = consecutive pixels
+        const bool split_t = p.out_planes == 2;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          umma::store_split(p.out_t + (ch0 + gi * 16 + j) * (long long)p.ld_t + pix, p.out_t_plane_stride,
+                            split_t ? 2 : 1, v[j]);
       }
       if (p.out_fp32) {
         float4* dst = (float4*)((float*)p.out + pix * p.Cout_total + ch0 + gi * 16);
@@ -418,7 +456,7 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
     if (r != CUDA_SUCCESS) return HIMO_ERR_ARG;
   }
   const int taps = d->ksize * d->ksize;
-  const long long k_total = (long long)taps * d->Cin;
+  const long long k_total = d->b_k_total > 0 ? d->b_k_total : (long long)taps * d->Cin;
   {
     cuuint64_t dims[3] = {(cuuint64_t)k_total, (cuuint64_t)d->Cout, (cuuint64_t)P};
     cuuint64_t strides[2] = {(cuuint64_t)k_total * 2, (cuuint64_t)d->Cout * k_total * 2};
@@ -439,6 +477,11 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
   p.cout_group_stride = d->cout_group_stride; p.act = d->act; p.out_fp32 = d->out_fp32;
   p.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
   p.flush_iters = g_flush_iters;   // k-iterations (2 hi*hi MMAs each) per TMEM accumulation chain
+  p.out_t = (__nv_bfloat16*)d->out_t; p.out_t_plane_stride = d->out_t_plane_stride; p.ld_t = d->ld_t;
+  p.mask_src = (const __nv_bfloat16*)d->mask_src; p.mask_plane_stride = d->mask_plane_stride;
+  p.mask_planes = d->mask_planes;
+  p.b_group_k_stride = d->b_group_k_stride; p.out_group_pix_stride = d->out_group_pix_stride;
+  p.stop_flag = d->stop_flag;
   const int n_ctas = p.tiles_x * p.tiles_y * p.n_tiles_n * groups;
 #define HIMO_CONV_CASE(bn, pp, st) \
   if (BN == bn && P == pp) return launch_conv<bn, BK, pp, st>(tmA, tmB, p, n_ctas, stream);

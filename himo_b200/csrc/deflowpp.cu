@@ -61,7 +61,7 @@ static size_t net_layout(int n_max, int planes, const float* vs, const float* cr
 static int conv(const Act& in, int cin_off, int cin, int groups, const void* w, const float* bias, int cout,
                 int ksize, int stride, int act, const Act& out, int cout_off, int planes, cudaStream_t stream,
                 float acc_scale, float* out_f32 = nullptr) {
-  himo_conv_desc d;
+  himo_conv_desc d = {};
   d.in = in.p; d.in_planes = planes; d.in_plane_stride = in.plane_stride();
   d.H_in = in.H; d.W_in = in.W; d.Cin_total = in.C; d.cin_off = cin_off; d.Cin = cin;
   d.wgt = w; d.bias = bias; d.Cout = cout; d.ksize = ksize; d.stride = stride;

@@ -1,0 +1,681 @@
+// himo_b200/csrc/nsf.cu -- H3: FastNSF per-frame-pair optimisation on the device.
+//
+// Replaces FastNSF.optimize (OSF/src/models/fastnsf.py:105-169) with its pieces
+//   DT.__init__ / FastGeodis.generalised_geodesic3d   fastnsf.py:30-57  (distance volume)
+//   DT.torch_bilinear_distance (+ autograd)            fastnsf.py:59-80  (trilinear lookup)
+//   Neural_Prior.forward (+ autograd)                  basic/nsfp_module.py:41-47 (3->128x8->3 ReLU MLP)
+//   torch.optim.Adam.step, EarlyStopping.step          fastnsf.py:134-164, nsfp_module.py:65-82
+// The reference runs ~60 launches and >= 2 host syncs per iteration.  Here one iteration is 34 launches
+// with no host involvement: the seven 128x128 hidden layers run forward, backward (dX) and weight-gradient
+// (dW, split-K) on the tcgen05 GEMM kernel of conv.cu with ReLU / ReLU-mask / transposed stores fused into
+// its epilogue; loss, best-flow snapshot, early stopping and Adam live in a device control block; the
+// host only polls a stop flag every few iterations.
+#include <math.h>
+
+#include "common.cuh"
+#include "himo_b200.h"
+#include "umma.cuh"
+
+namespace himo {
+
+constexpr int kNsfHidden = 128;
+constexpr int kNsfLayers = 8;                 // hidden layers (nn_layers.0 .. nn_layers.14)
+constexpr float kNsfWScale = 256.f;           // power-of-two prescale of the packed weights (split mode)
+
+struct NsfCtl {
+  int stop;            // set by the early-stopping state machine
+  int iters;           // iterations executed (loss evaluations)
+  int snapshot;        // this iteration's flow is the new best
+  int es_has_best;
+  int es_bad;
+  float best_loss;
+  float es_best;
+  float loss;
+};
+
+struct NsfVol {        // distance volume geometry (host + device copy)
+  float lo[3];
+  int dims[3];         // H, W, D  (x, y, z)
+  float gf;
+};
+
+// ------------------------------------------------------------------------------ DT: bounds
+__device__ __forceinline__ unsigned nsf_f2ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float nsf_ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__global__ void k_nsf_bbox_init(unsigned* b) {
+  if (threadIdx.x < 3) b[threadIdx.x] = 0xffffffffu;
+  else if (threadIdx.x < 6) b[threadIdx.x] = 0u;
+}
+__global__ void __launch_bounds__(256)
+k_nsf_bbox(const float* __restrict__ a, int na, const float* __restrict__ b, int nb, unsigned* __restrict__ bbox) {
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += gridDim.x * blockDim.x) {
+    const float* p = i < na ? a + 3 * (size_t)i : b + 3 * (size_t)(i - na);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { float v = __ldg(p + k); lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v); }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], d));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], d));
+    }
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (lo[k] <= hi[k]) { atomicMin(bbox + k, nsf_f2ord(lo[k])); atomicMax(bbox + 3 + k, nsf_f2ord(hi[k])); }
+}
+// lo = floor(min*gf - 1)/gf, hi = ceil(max*gf + 1)/gf, samples = ceil((hi-lo)*gf) + 2, all in fp32
+// (fastnsf.py:120-126 and DT.__init__ :34-36).
+__global__ void k_nsf_vol(const unsigned* __restrict__ bbox, float gf, NsfVol* __restrict__ v) {
+  if (threadIdx.x != 0) return;
+  for (int k = 0; k < 3; ++k) {
+    const float mn = nsf_ord2f(bbox[k]), mx = nsf_ord2f(bbox[3 + k]);
+    const float lo = __fdiv_rn(floorf(__fsub_rn(__fmul_rn(mn, gf), 1.f)), gf);
+    const float hi = __fdiv_rn(ceilf(__fadd_rn(__fmul_rn(mx, gf), 1.f)), gf);
+    v->lo[k] = lo;
+    v->dims[k] = (int)ceilf(__fmul_rn(__fsub_rn(hi, lo), gf)) + 2;
+  }
+  v->gf = gf;
+}
+
+// ------------------------------------------------------------------------------ DT: occupancy + raster passes
+__global__ void __launch_bounds__(256)
+k_nsf_fill(float* __restrict__ d, long long n, float v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = v;
+}
+__global__ void __launch_bounds__(256)
+k_nsf_occupancy(const float* __restrict__ pc1, int n, NsfVol v, float* __restrict__ d) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // index = round((p - V[0]) * gf), torch.round = half-to-even = cvt.rni (fastnsf.py:46-50)
+    const int ix = __float2int_rn(__fmul_rn(__fsub_rn(pc1[3 * (size_t)i], v.lo[0]), v.gf));
+    const int iy = __float2int_rn(__fmul_rn(__fsub_rn(pc1[3 * (size_t)i + 1], v.lo[1]), v.gf));
+    const int iz = __float2int_rn(__fmul_rn(__fsub_rn(pc1[3 * (size_t)i + 2], v.lo[2]), v.gf));
+    if (ix >= 0 && ix < v.dims[0] && iy >= 0 && iy < v.dims[1] && iz >= 0 && iz < v.dims[2])
+      d[((size_t)ix * v.dims[1] + iy) * v.dims[2] + iz] = 0.f;
+  }
+}
+
+// One raster pass of the FastGeodis Euclidean transform advances along `axis`; plane p takes
+//   new[p] = min(old[p], min over the 3x3 neighbourhood of new[p -/+ 1] + step length).
+// A block owns a 32x32 tile of the plane and advances kDtSteps planes per launch from a halo of kDtSteps
+// cells (the dependency cone widens by one cell per plane), so a pass costs n_axis/kDtSteps launches
+// instead of n_axis.  Halo cells may read a neighbour block's already-updated value of plane p; because
+// the update is an idempotent min over the same inputs this cannot change the result.
+constexpr int kDtSteps = 8;
+constexpr int kDtTile = 32;
+constexpr int kDtReg = kDtTile + 2 * kDtSteps;   // 48
+
+__global__ void __launch_bounds__(256)
+k_nsf_dt_pass(float* __restrict__ d, int n0, int n1, int n2, int axis, int dir, int p_begin, int count,
+              float l00, float l01, float l11) {
+  // l00 = straight step, l01 = one lateral move, l11 = two lateral moves
+  __shared__ float buf[2][kDtReg][kDtReg + 1];
+  const int n[3] = {n0, n1, n2};
+  const long long st[3] = {(long long)n1 * n2, (long long)n2, 1};
+  const int a = axis, h = (axis + 1) % 3, w = (axis + 2) % 3;
+  const int h0 = blockIdx.y * kDtTile - kDtSteps, w0 = blockIdx.x * kDtTile - kDtSteps;
+  const int pp = p_begin - dir;     // plane already final
+  for (int t = threadIdx.x; t < kDtReg * kDtReg; t += blockDim.x) {
+    const int rh = t / kDtReg, rw = t % kDtReg;
+    const int ih = h0 + rh, iw = w0 + rw;
+    float v = INFINITY;
+    if (ih >= 0 && ih < n[h] && iw >= 0 && iw < n[w]) v = d[pp * st[a] + ih * st[h] + iw * st[w]];
+    buf[0][rh][rw] = v;
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int s = 0; s < count; ++s) {
+    const int p = p_begin + s * dir;
+    const int shrink = s + 1;                       // cells still exact after s+1 steps
+    const int lo = shrink, hi = kDtReg - shrink;     // region [lo,hi) in both directions
+    const int side = hi - lo;
+    for (int t = threadIdx.x; t < side * side; t += blockDim.x) {
+      const int rh = lo + t / side, rw = lo + t % side;
+      const int ih = h0 + rh, iw = w0 + rw;
+      float best = INFINITY;
+      if (ih >= 0 && ih < n[h] && iw >= 0 && iw < n[w]) {
+        best = d[p * st[a] + ih * st[h] + iw * st[w]];
+#pragma unroll
+        for (int dh = -1; dh <= 1; ++dh)
+#pragma unroll
+          for (int dw = -1; dw <= 1; ++dw) {
+            const float step = (dh == 0 && dw == 0) ? l00 : ((dh != 0 && dw != 0) ? l11 : l01);
+            best = fminf(best, __fadd_rn(buf[cur][rh + dh][rw + dw], step));
+          }
+        if (rh >= kDtSteps && rh < kDtSteps + kDtTile && rw >= kDtSteps && rw < kDtSteps + kDtTile)
+          d[p * st[a] + ih * st[h] + iw * st[w]] = best;
+      }
+      buf[cur ^ 1][rh][rw] = best;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+
+// ------------------------------------------------------------------------------ MLP pieces outside the GEMMs
+struct NsfBufs {
+  const float4* x4;                // [n_pad] source points (xyz, 0)
+  int n, n_pad;
+  int planes;
+  long long ps;                    // plane stride of the [n_pad][128] / [128][n_pad] tensors
+  __nv_bfloat16* H[kNsfLayers + 1];    // H[l], l = 1..8: activations row-major planes
+  __nv_bfloat16* HT[kNsfLayers + 1];   // transposed planes
+  __nv_bfloat16* DL[2];
+  __nv_bfloat16* DLT[2];
+  float* params;                   // master fp32 parameters, reference layout
+  float* flow;                     // [n_pad][4]
+  float* best_flow;                // [n_pad][4]
+  float* head_part;                // [head_blocks][kHeadPart]
+  float* gW0;                      // [128][3] + [128] bias
+  float* gb;                       // [7][128] bias grads of layers 1..7 (scaled)
+  NsfCtl* ctl;
+  float grad_scale;                // power of two S; every backward tensor carries S/N instead of 1/N
+};
+
+// parameter offsets in the flat master array (reference state_dict order)
+__host__ __device__ inline int nsf_off_w(int l) {   // l = 0..8
+  if (l == 0) return 0;
+  return 128 * 3 + 128 + (l - 1) * (128 * 128 + 128);
+}
+__host__ __device__ inline int nsf_off_b(int l) {
+  if (l == 0) return 128 * 3;
+  if (l == 8) return nsf_off_w(8) + 3 * 128;
+  return nsf_off_w(l) + 128 * 128;
+}
+constexpr int kNsfParams = 128 * 3 + 128 + 7 * (128 * 128 + 128) + 3 * 128 + 3;   // 116483
+
+// layer 0: h1 = relu(W0 x + b0), K = 3 -> plain FMAs; writes row-major and transposed planes
+__global__ void __launch_bounds__(256)
+k_nsf_l0_fwd(NsfBufs b) {
+  if (b.ctl->stop) return;
+  const float* W = b.params + nsf_off_w(0);
+  const float* bias = b.params + nsf_off_b(0);
+  const long long total = (long long)b.n_pad * 128;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(t % 128);
+    const long long i = t / 128;
+    const float4 p = b.x4[i];
+    float v = __ldg(W + j * 3) * p.x;
+    v = fmaf(__ldg(W + j * 3 + 1), p.y, v);
+    v = fmaf(__ldg(W + j * 3 + 2), p.z, v);
+    v = fmaxf(v + __ldg(bias + j), 0.f);
+    umma::store_split(b.H[1] + i * 128 + j, b.ps, b.planes, v);
+    umma::store_split(b.HT[1] + (long long)j * b.n_pad + i, b.ps, b.planes, v);
+  }
+}
+
+__device__ __forceinline__ float load_split(const __nv_bfloat16* p, long long ps, int planes) {
+  if (planes == 2) {
+    const __half* h = reinterpret_cast<const __half*>(p);
+    return __half2float(h[0]) + __half2float(h[ps]);
+  }
+  return __bfloat162float(p[0]);
+}
+
+constexpr int kHeadThreads = 128;
+constexpr int kHeadPart = 3 * 128 + 3 + 1;   // dW8, db8, loss
+
+// Output layer + loss + its backward, one thread per point:
+//   flow = W8 h8 + b8; Y = x + flow; loss_i = trilinear D(Y); dflow = grad_Y D * (S/N)
+//   dh8 = (dflow . W8) * relu'(h8); per-block partial sums of dW8, db8 and the loss.
+__global__ void __launch_bounds__(kHeadThreads)
+k_nsf_head(NsfBufs b, const float* __restrict__ D, NsfVol vol) {
+  if (b.ctl->stop) return;
+  __shared__ float red[kHeadThreads / 32][4];
+  const float* W8 = b.params + nsf_off_w(8);
+  const float* b8 = b.params + nsf_off_b(8);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < b.n;
+  const int ii = live ? i : 0;
+  const __nv_bfloat16* hT = b.HT[8];
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+  for (int j = 0; j < 128; ++j) {
+    const float h = load_split(hT + (long long)j * b.n_pad + ii, b.ps, b.planes);
+    f0 = fmaf(__ldg(W8 + j), h, f0);
+    f1 = fmaf(__ldg(W8 + 128 + j), h, f1);
+    f2 = fmaf(__ldg(W8 + 256 + j), h, f2);
+  }
+  f0 += __ldg(b8); f1 += __ldg(b8 + 1); f2 += __ldg(b8 + 2);
+  const float4 x = b.x4[ii];
+  const float Y[3] = {x.x + f0, x.y + f1, x.z + f2};
+  // DT.torch_bilinear_distance (fastnsf.py:59-80) followed by grid_sample's own un-normalisation
+  float ix[3], pass[3];
+  int i0[3];
+  float fr[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float sz = (float)(vol.dims[k] - 1);
+    const float raw = __fmul_rn(__fsub_rn(Y[k], vol.lo[k]), vol.gf);
+    const float s = fminf(fmaxf(raw, 0.f), sz);
+    pass[k] = (raw >= 0.f && raw <= sz) ? vol.gf : 0.f;          // d clip / dY
+    const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, s), sz), 1.f);
+    ix[k] = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), sz);
+    const float fl = floorf(ix[k]);
+    i0[k] = (int)fl;
+    fr[k] = ix[k] - fl;
+  }
+  float val = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
+    const int cx = i0[0] + dx, cy = i0[1] + dy, cz = i0[2] + dz;
+    float dv = 0.f;   // zero padding outside the volume
+    if (cx >= 0 && cx < vol.dims[0] && cy >= 0 && cy < vol.dims[1] && cz >= 0 && cz < vol.dims[2])
+      dv = __ldg(D + ((size_t)cx * vol.dims[1] + cy) * vol.dims[2] + cz);
+    const float wx = dx ? fr[0] : 1.f - fr[0], wy = dy ? fr[1] : 1.f - fr[1], wz = dz ? fr[2] : 1.f - fr[2];
+    val = fmaf(dv, wx * wy * wz, val);
+    gx = fmaf(dv, (dx ? 1.f : -1.f) * wy * wz, gx);
+    gy = fmaf(dv, (dy ? 1.f : -1.f) * wx * wz, gy);
+    gz = fmaf(dv, (dz ? 1.f : -1.f) * wx * wy, gz);
+  }
+  // d ix / dY = (sz/2) * (2/sz) * gf * [inside] = gf * [inside]
+  const float sN = b.grad_scale / (float)b.n;
+  float d0 = live ? gx * pass[0] * sN : 0.f, d1 = live ? gy * pass[1] * sN : 0.f, d2 = live ? gz * pass[2] * sN : 0.f;
+  if (!live) val = 0.f;
+  if (live) *(float4*)(b.flow + 4 * (size_t)i) = make_float4(f0, f1, f2, val);
+  // backward through the output layer + ReLU mask of h8
+  float* part = b.head_part + (size_t)blockIdx.x * kHeadPart;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = 0; j < 128; ++j) {
+    const float h = i < b.n_pad ? load_split(hT + (long long)j * b.n_pad + (i < b.n_pad ? i : 0), b.ps, b.planes) : 0.f;
+    float dh = fmaf(d2, __ldg(W8 + 256 + j), fmaf(d1, __ldg(W8 + 128 + j), d0 * __ldg(W8 + j)));
+    if (!(h > 0.f)) dh = 0.f;
+    if (i < b.n_pad) {
+      umma::store_split(b.DL[0] + (long long)i * 128 + j, b.ps, b.planes, dh);
+      umma::store_split(b.DLT[0] + (long long)j * b.n_pad + i, b.ps, b.planes, dh);
+    }
+    // dW8[k][j] partial = sum over the block's points of d_k * h_j (fixed shuffle tree => deterministic)
+    float a0 = d0 * h, a1 = d1 * h, a2 = d2 * h;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, s);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, s);
+    }
+    if (lane == 0) { red[warp][0] = a0; red[warp][1] = a1; red[warp][2] = a2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float s = 0.f;
+      for (int wv = 0; wv < kHeadThreads / 32; ++wv) s += red[wv][threadIdx.x];
+      part[threadIdx.x * 128 + j] = s;
+    }
+    __syncthreads();
+  }
+  float a0 = d0, a1 = d1, a2 = d2, a3 = val;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, s);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, s);
+    a3 += __shfl_xor_sync(0xffffffffu, a3, s);
+  }
+  if (lane == 0) { red[warp][0] = a0; red[warp][1] = a1; red[warp][2] = a2; red[warp][3] = a3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+    for (int wv = 0; wv < kHeadThreads / 32; ++wv) s += red[wv][threadIdx.x];
+    part[384 + threadIdx.x] = s;
+  }
+}
+
+// loss reduction + best-flow bookkeeping + EarlyStopping.step (nsfp_module.py:65-82), single thread.
+__global__ void k_nsf_control(NsfBufs b, int head_blocks, float min_delta, int patience) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  NsfCtl* c = b.ctl;
+  if (c->stop) { c->snapshot = 0; return; }
+  double s = 0.0;
+  for (int k = 0; k < head_blocks; ++k) s += (double)b.head_part[(size_t)k * kHeadPart + 387];
+  const float loss = (float)(s / (double)b.n);
+  c->loss = loss;
+  c->iters += 1;
+  c->snapshot = 0;
+  if (loss <= c->best_loss) { c->best_loss = loss; c->snapshot = 1; }     // fastnsf.py:151-153
+  int stop = 0;
+  if (!c->es_has_best) { c->es_has_best = 1; c->es_best = loss; }
+  else if (isnan(loss)) stop = 1;
+  else {
+    if (loss < c->es_best - min_delta) { c->es_bad = 0; c->es_best = loss; }
+    else c->es_bad += 1;
+    if (c->es_bad >= patience) stop = 1;
+  }
+  c->stop = stop;
+}
+
+__global__ void __launch_bounds__(256)
+k_nsf_snapshot(NsfBufs b) {
+  if (!b.ctl->snapshot) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += gridDim.x * blockDim.x)
+    *(float4*)(b.best_flow + 4 * (size_t)i) = *(const float4*)(b.flow + 4 * (size_t)i);
+}
+
+// bias gradient of layer l (1..7) = row sums of delta_{l+1}^T; for layer 0 also dW0 = delta_1^T x.
+// One block per feature, fixed-order tree => deterministic.
+__global__ void __launch_bounds__(256)
+k_nsf_rowsum(NsfBufs b, const __nv_bfloat16* __restrict__ dT, float* __restrict__ out_b, float* __restrict__ out_w0) {
+  if (b.ctl->stop) return;
+  __shared__ float red[8][4];
+  const int f = blockIdx.x;
+  float s = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int i = threadIdx.x; i < b.n; i += blockDim.x) {
+    const float v = load_split(dT + (long long)f * b.n_pad + i, b.ps, b.planes);
+    s += v;
+    if (out_w0) { const float4 p = b.x4[i]; sx = fmaf(v, p.x, sx); sy = fmaf(v, p.y, sy); sz = fmaf(v, p.z, sz); }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+    sx += __shfl_xor_sync(0xffffffffu, sx, d);
+    sy += __shfl_xor_sync(0xffffffffu, sy, d);
+    sz += __shfl_xor_sync(0xffffffffu, sz, d);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[warp][0] = s; red[warp][1] = sx; red[warp][2] = sy; red[warp][3] = sz; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int wv = 0; wv < 8; ++wv) for (int k = 0; k < 4; ++k) t[k] += red[wv][k];
+    out_b[f] = t[0];
+    if (out_w0) { out_w0[f * 3] = t[1]; out_w0[f * 3 + 1] = t[2]; out_w0[f * 3 + 2] = t[3]; }
+  }
+}
+
+struct NsfAdamArgs {
+  float* params; float* m; float* v;
+  const float* dW_part;      // [7][splits][128][128]
+  int splits;
+  const float* gb;           // [7][128]
+  const float* gW0;          // [128][3]
+  const float* gb0;          // [128]
+  const float* head_part; int head_blocks;
+  __nv_bfloat16* Wp[kNsfLayers];    // packed [P][128][128] weights of layers 1..7 (index l)
+  __nv_bfloat16* WpT[kNsfLayers];   // packed transposes
+  int planes;
+  float lr, beta1, beta2, eps, inv_scale;
+  const NsfCtl* ctl;
+};
+
+// torch.optim.Adam.step (amsgrad=False, weight_decay=0, maximize=False) for every parameter, then the
+// repack of the hidden-layer weights into the GEMM operand planes.
+__global__ void __launch_bounds__(256)
+k_nsf_adam(NsfAdamArgs a) {
+  if (a.ctl->stop) return;
+  const int step = a.ctl->iters;           // 1-based: the control kernel has already counted this iteration
+  const float bc1 = 1.f - powf(a.beta1, (float)step), bc2 = 1.f - powf(a.beta2, (float)step);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < kNsfParams; t += gridDim.x * blockDim.x) {
+    // locate the parameter and gather its (scaled) gradient
+    float g = 0.f;
+    int layer = -1, r = 0, c = 0;
+    bool is_w = false;
+    if (t < 384) { g = a.gW0[t]; }
+    else if (t < 512) { g = a.gb0[t - 384]; }
+    else if (t >= nsf_off_w(8)) {
+      const int k = t - nsf_off_w(8);       // dW8 [3][128] then db8 [3]
+      for (int blk = 0; blk < a.head_blocks; ++blk) g += a.head_part[(size_t)blk * kHeadPart + k];
+    } else {
+      const int u = t - 512;
+      layer = 1 + u / (128 * 128 + 128);
+      const int w = u % (128 * 128 + 128);
+      if (w < 128 * 128) {
+        is_w = true; r = w / 128; c = w % 128;
+        const float* p = a.dW_part + ((size_t)(layer - 1) * a.splits) * 16384 + w;
+        for (int s = 0; s < a.splits; ++s) g += p[(size_t)s * 16384];
+      } else {
+        g = a.gb[(layer - 1) * 128 + (w - 128 * 128)];
+      }
+    }
+    g *= a.inv_scale;
+    const float m = a.beta1 * a.m[t] + (1.f - a.beta1) * g;          // exp_avg.lerp_(grad, 1-beta1)
+    const float v = a.beta2 * a.v[t] + (1.f - a.beta2) * g * g;      // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
+    a.m[t] = m; a.v[t] = v;
+    const float denom = sqrtf(v) / sqrtf(bc2) + a.eps;
+    const float pnew = a.params[t] - (a.lr / bc1) * (m / denom);
+    a.params[t] = pnew;
+    if (is_w) {
+      const float scaled = a.planes == 2 ? pnew * kNsfWScale : pnew;
+      umma::store_split(a.Wp[layer] + r * 128 + c, 16384, a.planes, scaled);
+      umma::store_split(a.WpT[layer] + c * 128 + r, 16384, a.planes, scaled);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_nsf_pack_weights(const float* __restrict__ params, NsfAdamArgs a) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 7 * 16384; t += gridDim.x * blockDim.x) {
+    const int layer = 1 + t / 16384, w = t % 16384, r = w / 128, c = w % 128;
+    const float pv = params[nsf_off_w(layer) + w];
+    const float scaled = a.planes == 2 ? pv * kNsfWScale : pv;
+    umma::store_split(a.Wp[layer] + r * 128 + c, 16384, a.planes, scaled);
+    umma::store_split(a.WpT[layer] + c * 128 + r, 16384, a.planes, scaled);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_nsf_pack_points(const float* __restrict__ pc, int n, int n_pad, float4* __restrict__ x4) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+    x4[i] = i < n ? make_float4(pc[3 * (size_t)i], pc[3 * (size_t)i + 1], pc[3 * (size_t)i + 2], 0.f)
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+k_nsf_unpack_flow(const float* __restrict__ f4, int n, float* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    out[3 * (size_t)i] = f4[4 * (size_t)i]; out[3 * (size_t)i + 1] = f4[4 * (size_t)i + 1];
+    out[3 * (size_t)i + 2] = f4[4 * (size_t)i + 2];
+  }
+}
+
+struct NsfLayout {
+  NsfBufs b;
+  NsfAdamArgs ad;
+  float* dW_part; int splits; int k_split;
+  unsigned* bbox; NsfVol* vol_dev;
+  int head_blocks;
+};
+
+static size_t nsf_layout(int n_max, int planes, NsfLayout* L, void* base) {
+  Arena A(base, (size_t)-1);
+  const int n_pad = ceil_div(n_max > 0 ? n_max : 1, 128) * 128;
+  const size_t act = (size_t)planes * n_pad * 128;
+  NsfLayout l;
+  l.b.x4 = A.take<float4>(n_pad);
+  for (int k = 1; k <= kNsfLayers; ++k) { l.b.H[k] = A.take<__nv_bfloat16>(act); l.b.HT[k] = A.take<__nv_bfloat16>(act); }
+  l.b.H[0] = l.b.HT[0] = nullptr;
+  for (int k = 0; k < 2; ++k) { l.b.DL[k] = A.take<__nv_bfloat16>(act); l.b.DLT[k] = A.take<__nv_bfloat16>(act); }
+  l.b.params = A.take<float>(kNsfParams);
+  l.ad.m = A.take<float>(kNsfParams);
+  l.ad.v = A.take<float>(kNsfParams);
+  l.b.flow = A.take<float>((size_t)n_pad * 4);
+  l.b.best_flow = A.take<float>((size_t)n_pad * 4);
+  l.head_blocks = ceil_div(n_pad, kHeadThreads);
+  l.b.head_part = A.take<float>((size_t)l.head_blocks * kHeadPart);
+  l.b.gW0 = A.take<float>(128 * 3 + 128);
+  l.b.gb = A.take<float>(7 * 128);
+  l.b.ctl = A.take<NsfCtl>(1);
+  l.k_split = 32 * ceil_div(n_pad, 32 * kNumSMs);
+  l.splits = ceil_div(n_pad, l.k_split);
+  l.dW_part = A.take<float>((size_t)7 * l.splits * 16384);
+  for (int k = 1; k < kNsfLayers; ++k) {
+    l.ad.Wp[k] = A.take<__nv_bfloat16>((size_t)planes * 16384);
+    l.ad.WpT[k] = A.take<__nv_bfloat16>((size_t)planes * 16384);
+  }
+  l.ad.Wp[0] = l.ad.WpT[0] = nullptr;
+  l.bbox = A.take<unsigned>(8);
+  l.vol_dev = A.take<NsfVol>(1);
+  if (L) *L = l;
+  return A.off + 1024;
+}
+
+#define HIMO_RET(expr) do { int _s = (expr); if (_s != HIMO_OK) return _s; } while (0)
+
+static int nsf_gemm(const himo_conv_desc& d, cudaStream_t stream) { return himo_conv2d_nhwc(&d, stream); }
+
+}  // namespace himo
+
+using namespace himo;
+
+extern "C" size_t himo_nsf_workspace_bytes(int n_max, int planes) {
+  if (n_max < 0 || (planes != 1 && planes != 2)) return 0;
+  return nsf_layout(n_max, planes, nullptr, nullptr);
+}
+
+// Distance-volume geometry of a frame pair: host gets lo[3], dims[3] (one small synchronous copy per
+// frame pair; the reference syncs >= 2x per ITERATION).
+extern "C" int himo_nsf_volume_geometry(const float* pc0, int n0, const float* pc1, int n1, float grid_factor,
+                                        float* lo_host, int32_t* dims_host, void* workspace, void* stream_) {
+  if (n0 <= 0 || n1 <= 0 || !pc0 || !pc1 || !workspace || !lo_host || !dims_host) return HIMO_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  unsigned* bbox = (unsigned*)workspace;
+  NsfVol* vd = (NsfVol*)((char*)workspace + 256);
+  k_nsf_bbox_init<<<1, 32, 0, stream>>>(bbox); HIMO_LAUNCH_RET();
+  k_nsf_bbox<<<min(ceil_div(n0 + n1, 256), kNumSMs * 4), 256, 0, stream>>>(pc0, n0, pc1, n1, bbox); HIMO_LAUNCH_RET();
+  k_nsf_vol<<<1, 32, 0, stream>>>(bbox, grid_factor, vd); HIMO_LAUNCH_RET();
+  NsfVol hv;
+  HIMO_CUDA_RET(cudaMemcpyAsync(&hv, vd, sizeof(NsfVol), cudaMemcpyDeviceToHost, stream));
+  HIMO_CUDA_RET(cudaStreamSynchronize(stream));
+  for (int k = 0; k < 3; ++k) { lo_host[k] = hv.lo[k]; dims_host[k] = hv.dims[k]; }
+  return HIMO_OK;
+}
+
+// D[H][W][D] = FastGeodis-style raster Euclidean distance transform of the occupancy of pc1.
+extern "C" int himo_nsf_dt_build(const float* pc1, int n1, const float* lo, const int32_t* dims, float grid_factor,
+                                 float* D, void* stream_) {
+  if (!pc1 || n1 < 0 || !lo || !dims || !D) return HIMO_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NsfVol v;
+  for (int k = 0; k < 3; ++k) { v.lo[k] = lo[k]; v.dims[k] = dims[k]; if (dims[k] <= 0) return HIMO_ERR_ARG; }
+  v.gf = grid_factor;
+  const long long total = (long long)dims[0] * dims[1] * dims[2];
+  k_nsf_fill<<<kNumSMs * 8, 256, 0, stream>>>(D, total, 1e10f); HIMO_LAUNCH_RET();
+  if (n1 > 0) { k_nsf_occupancy<<<min(ceil_div(n1, 256), kNumSMs * 8), 256, 0, stream>>>(pc1, n1, v, D); HIMO_LAUNCH_RET(); }
+  const float sp = 1.0f / grid_factor;
+  const float l00 = sqrtf(sp * sp), l01 = sqrtf(sp * sp + sp * sp), l11 = sqrtf(sp * sp + sp * sp + sp * sp);
+  const int n[3] = {dims[0], dims[1], dims[2]};
+  for (int axis = 0; axis < 3; ++axis) {
+    const int h = (axis + 1) % 3, w = (axis + 2) % 3;
+    dim3 grid(ceil_div(n[w], kDtTile), ceil_div(n[h], kDtTile));
+    for (int dir = 1; dir >= -1; dir -= 2) {
+      int p = dir > 0 ? 1 : n[axis] - 2;
+      int remaining = n[axis] - 1;
+      while (remaining > 0) {
+        const int cnt = remaining < kDtSteps ? remaining : kDtSteps;
+        k_nsf_dt_pass<<<grid, 256, 0, stream>>>(D, n[0], n[1], n[2], axis, dir, p, cnt, l00, l01, l11);
+        HIMO_LAUNCH_RET();
+        p += dir * cnt;
+        remaining -= cnt;
+      }
+    }
+  }
+  return HIMO_OK;
+}
+
+// The optimisation loop.  Blocking call (it polls the device stop flag every `poll` iterations).
+extern "C" int himo_nsf_optimize(const himo_nsf_desc* d, void* stream_) {
+  if (!d || !d->pc0 || d->n <= 0 || !d->D || !d->init_params || !d->best_flow || !d->workspace) return HIMO_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int P = d->planes;
+  if (P != 1 && P != 2) return HIMO_ERR_ARG;
+  NsfLayout L;
+  if (nsf_layout(d->n_max, P, &L, d->workspace) > d->workspace_bytes || d->n > d->n_max) return HIMO_ERR_WORKSPACE;
+  const int n = d->n, n_pad = ceil_div(n, 128) * 128;
+  NsfBufs b = L.b;
+  b.n = n; b.n_pad = n_pad; b.planes = P; b.ps = (long long)n_pad * 128;
+  int e = 0; while ((1 << e) < n) ++e;
+  b.grad_scale = (float)(1 << e);
+  NsfVol vol;
+  for (int k = 0; k < 3; ++k) { vol.lo[k] = d->lo[k]; vol.dims[k] = d->dims[k]; }
+  vol.gf = d->grid_factor;
+  const int head_blocks = ceil_div(n_pad, kHeadThreads);
+  const int k_split = 32 * ceil_div(n_pad, 32 * kNumSMs);
+  const int splits = ceil_div(n_pad, k_split);
+
+  NsfAdamArgs ad = L.ad;
+  ad.params = b.params; ad.dW_part = L.dW_part; ad.splits = splits; ad.gb = b.gb; ad.gW0 = b.gW0; ad.gb0 = b.gW0 + 384;
+  ad.head_part = b.head_part; ad.head_blocks = head_blocks; ad.planes = P;
+  ad.lr = d->lr; ad.beta1 = 0.9f; ad.beta2 = 0.999f; ad.eps = 1e-8f; ad.inv_scale = 1.0f / b.grad_scale; ad.ctl = b.ctl;
+
+  // ---- state init
+  HIMO_CUDA_RET(cudaMemcpyAsync(b.params, d->init_params, sizeof(float) * kNsfParams, cudaMemcpyDeviceToDevice, stream));
+  HIMO_CUDA_RET(cudaMemsetAsync(ad.m, 0, sizeof(float) * kNsfParams, stream));
+  HIMO_CUDA_RET(cudaMemsetAsync(ad.v, 0, sizeof(float) * kNsfParams, stream));
+  NsfCtl c0 = {};
+  c0.best_loss = INFINITY;
+  HIMO_CUDA_RET(cudaMemcpyAsync(b.ctl, &c0, sizeof(NsfCtl), cudaMemcpyHostToDevice, stream));
+  HIMO_CUDA_RET(cudaMemsetAsync(b.best_flow, 0, sizeof(float) * 4 * n_pad, stream));
+  k_nsf_pack_points<<<min(ceil_div(n_pad, 256), kNumSMs * 8), 256, 0, stream>>>(d->pc0, n, n_pad, (float4*)b.x4);
+  HIMO_LAUNCH_RET();
+  k_nsf_pack_weights<<<kNumSMs * 2, 256, 0, stream>>>(b.params, ad);
+  HIMO_LAUNCH_RET();
+
+  const float wscale = P == 2 ? 1.0f / kNsfWScale : 1.0f;
+  auto iteration = [&]() -> int {
+    k_nsf_l0_fwd<<<kNumSMs * 8, 256, 0, stream>>>(b); HIMO_LAUNCH_RET();
+    for (int l = 1; l < kNsfLayers; ++l) {                      // h_{l+1} = relu(W_l h_l + b_l)
+      himo_conv_desc g = {};
+      g.in = b.H[l]; g.in_planes = P; g.in_plane_stride = b.ps; g.H_in = n_pad / 128; g.W_in = 128;
+      g.Cin_total = 128; g.Cin = 128; g.wgt = ad.Wp[l]; g.bias = b.params + nsf_off_b(l); g.Cout = 128; g.ksize = 1;
+      g.stride = 1; g.out = b.H[l + 1]; g.out_planes = P; g.out_plane_stride = b.ps; g.Cout_total = 128; g.act = 4;
+      g.n_groups = 1; g.acc_scale = wscale; g.out_t = b.HT[l + 1]; g.out_t_plane_stride = b.ps; g.ld_t = n_pad;
+      g.stop_flag = &b.ctl->stop;
+      HIMO_RET(nsf_gemm(g, stream));
+    }
+    k_nsf_head<<<head_blocks, kHeadThreads, 0, stream>>>(b, d->D, vol); HIMO_LAUNCH_RET();
+    k_nsf_control<<<1, 32, 0, stream>>>(b, head_blocks, d->min_delta, d->patience); HIMO_LAUNCH_RET();
+    k_nsf_snapshot<<<min(ceil_div(n, 256), kNumSMs * 4), 256, 0, stream>>>(b); HIMO_LAUNCH_RET();
+    int cur = 0;
+    for (int l = kNsfLayers - 1; l >= 1; --l) {
+      // dW_l = delta_{l+1}^T h_l  (split-K over the points), db_l = row sums of delta_{l+1}^T
+      himo_conv_desc g = {};
+      g.in = b.DLT[cur]; g.in_planes = P; g.in_plane_stride = b.ps; g.H_in = 1; g.W_in = 128;
+      g.Cin_total = n_pad; g.Cin = k_split; g.wgt = b.HT[l]; g.bias = nullptr; g.Cout = 128; g.ksize = 1; g.stride = 1;
+      g.out = L.dW_part + (size_t)(l - 1) * splits * 16384; g.out_fp32 = 1; g.out_planes = 1; g.Cout_total = 128;
+      g.n_groups = splits; g.cin_group_stride = k_split; g.cout_group_stride = 0; g.acc_scale = 1.f;
+      g.b_group_k_stride = k_split; g.out_group_pix_stride = 128; g.b_k_total = n_pad; g.stop_flag = &b.ctl->stop;
+      HIMO_RET(nsf_gemm(g, stream));
+      k_nsf_rowsum<<<128, 256, 0, stream>>>(b, b.DLT[cur], b.gb + (l - 1) * 128, nullptr); HIMO_LAUNCH_RET();
+      // delta_l = (delta_{l+1} W_l) * relu'(h_l)
+      himo_conv_desc q = {};
+      q.in = b.DL[cur]; q.in_planes = P; q.in_plane_stride = b.ps; q.H_in = n_pad / 128; q.W_in = 128;
+      q.Cin_total = 128; q.Cin = 128; q.wgt = ad.WpT[l]; q.bias = nullptr; q.Cout = 128; q.ksize = 1; q.stride = 1;
+      q.out = b.DL[cur ^ 1]; q.out_planes = P; q.out_plane_stride = b.ps; q.Cout_total = 128; q.act = 0;
+      q.n_groups = 1; q.acc_scale = wscale; q.out_t = b.DLT[cur ^ 1]; q.out_t_plane_stride = b.ps; q.ld_t = n_pad;
+      q.mask_src = b.H[l]; q.mask_plane_stride = b.ps; q.mask_planes = P; q.stop_flag = &b.ctl->stop;
+      HIMO_RET(nsf_gemm(q, stream));
+      cur ^= 1;
+    }
+    k_nsf_rowsum<<<128, 256, 0, stream>>>(b, b.DLT[cur], b.gW0 + 384, b.gW0); HIMO_LAUNCH_RET();
+    k_nsf_adam<<<kNumSMs * 2, 256, 0, stream>>>(ad); HIMO_LAUNCH_RET();
+    return HIMO_OK;
+  };
+
+  NsfCtl hc = {};
+  const int poll = d->poll_iters > 0 ? d->poll_iters : 8;
+  int launched = 0;
+  while (launched < d->max_iters) {
+    const int chunk = (d->max_iters - launched) < poll ? (d->max_iters - launched) : poll;
+    for (int k = 0; k < chunk; ++k) HIMO_RET(iteration());
+    launched += chunk;
+    HIMO_CUDA_RET(cudaMemcpyAsync(&hc, b.ctl, sizeof(NsfCtl), cudaMemcpyDeviceToHost, stream));
+    HIMO_CUDA_RET(cudaStreamSynchronize(stream));
+    if (hc.stop) break;
+  }
+  k_nsf_unpack_flow<<<min(ceil_div(n, 256), kNumSMs * 4), 256, 0, stream>>>(b.best_flow, n, d->best_flow);
+  HIMO_LAUNCH_RET();
+  if (d->final_params)
+    HIMO_CUDA_RET(cudaMemcpyAsync(d->final_params, b.params, sizeof(float) * kNsfParams, cudaMemcpyDeviceToDevice, stream));
+  if (d->exp_avg_out)
+    HIMO_CUDA_RET(cudaMemcpyAsync(d->exp_avg_out, ad.m, sizeof(float) * kNsfParams, cudaMemcpyDeviceToDevice, stream));
+  HIMO_CUDA_RET(cudaStreamSynchronize(stream));
+  if (d->iterations_out) *d->iterations_out = hc.iters;
+  if (d->best_loss_out) *d->best_loss_out = hc.best_loss;
+  if (d->last_loss_out) *d->last_loss_out = hc.loss;
+  return HIMO_OK;
+}

@@ -107,7 +107,7 @@ int himo_chamfer_backward(const float* pc0, int n0, const float* pc1, int n1, co
  *   bias    [Cout] f32 or NULL (BatchNorm folded in by the host)
  *   out     NHWC, channels [cout_off + g*cout_group_stride, +Cout) of Cout_total; bf16 planes
  *           (out_planes 1|2) or fp32 (out_fp32 = 1)
- *   ksize 1|3 (padding ksize/2), stride 1|2, act 0 none | 1 exact-erf GELU | 2 sigmoid | 3 tanh
+ *   ksize 1|3 (padding ksize/2), stride 1|2, act 0 none | 1 exact-erf GELU | 2 sigmoid | 3 tanh | 4 ReLU
  */
 typedef struct himo_conv_desc {
   const void* in;
@@ -124,6 +124,17 @@ typedef struct himo_conv_desc {
   int out_fp32, act;
   int n_groups, cin_group_stride, cout_group_stride;
   float acc_scale;            /* accumulator multiplier before bias/activation; 0 means 1 */
+  /* --- GEMM extensions (all optional, zero = off); used by the FastNSF MLP ------------------ */
+  void* out_t;                /* transposed copy of the output: [planes][Cout_total][ld_t] */
+  long long out_t_plane_stride;
+  int ld_t;
+  const void* mask_src;       /* ReLU-backward mask: output zeroed where this tensor (layout of out) is 0 */
+  long long mask_plane_stride;
+  int mask_planes;
+  int b_group_k_stride;       /* split-K: K offset of the weight operand per group */
+  long long out_group_pix_stride; /* split-K: output row offset per group */
+  long long b_k_total;        /* row length of the weight operand when it is not ksize^2*Cin */
+  const int32_t* stop_flag;   /* device flag; non-zero makes the launch a no-op (early stopping) */
 } himo_conv_desc;
 int himo_conv2d_nhwc(const himo_conv_desc* desc, void* stream);
 /* Split-mode accuracy/speed knob: k-iterations (32 input channels each) accumulated in tensor memory
@@ -243,6 +254,41 @@ int himo_rigid_flow(const float* points, int n, const float* T12_dev, const floa
  * src = index of point i in the ground-free cloud (NULL = identity). */
 int himo_final_flow(const float* points_all, int n_all, const float* T12_dev, const float* flow,
                     const int32_t* src_index, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * H3  FastNSF: distance volume + per-frame-pair MLP optimisation
+ * replaces: FastNSF.optimize (OSF/src/models/fastnsf.py:105-169) = DT.__init__ (:30-57, which calls the
+ *           third-party FastGeodis.generalised_geodesic3d), DT.torch_bilinear_distance (:59-80),
+ *           Neural_Prior.forward + autograd (OSF/src/models/basic/nsfp_module.py:7-47), torch.optim.Adam
+ *           and EarlyStopping.step (nsfp_module.py:51-97).
+ * himo_nsf_volume_geometry: lo = floor(min*gf-1)/gf and dims = ceil((hi-lo)*gf)+2 over both clouds
+ *   (fastnsf.py:120-126, :34-36); returns them to the HOST (one small sync per frame pair).
+ *   workspace: >= 1 KiB of device scratch.
+ * himo_nsf_dt_build: D[dims0][dims1][dims2] f32 = raster Euclidean transform (FastGeodis semantics,
+ *   lamb = 0, v = 1e10, 1 iteration) of the occupancy of pc1 at round((p - lo)*gf).
+ * himo_nsf_optimize: runs up to max_iters iterations with early stopping on the device and writes the
+ *   best flow [n,3].  init_params / final_params: DEVICE float[116483] in the reference's state_dict
+ *   order (W0[128,3], b0, W1[128,128], b1, ..., W7, b7, W8[3,128], b8).  Blocking call.
+ */
+#define HIMO_NSF_NUM_PARAMS 116483
+typedef struct himo_nsf_desc {
+  const float* pc0; int n;            /* ego-compensated, range-limited source cloud */
+  int n_max;                          /* workspace capacity in points */
+  const float* D; float lo[3]; int32_t dims[3]; float grid_factor;
+  const float* init_params; float* final_params;
+  float* exp_avg_out;                 /* optional DEVICE float[116483]: Adam first moment at exit (tests) */
+  int planes;                         /* 2 = split fp16 (fp32-class), 1 = bf16 */
+  int max_iters; float lr; float min_delta; int patience; int poll_iters;
+  float* best_flow;                   /* [n,3] */
+  int32_t* iterations_out; float* best_loss_out; float* last_loss_out;   /* HOST, optional */
+  void* workspace; size_t workspace_bytes;
+} himo_nsf_desc;
+size_t himo_nsf_workspace_bytes(int n_max, int planes);
+int himo_nsf_volume_geometry(const float* pc0, int n0, const float* pc1, int n1, float grid_factor,
+                             float* lo_host, int32_t* dims_host, void* workspace, void* stream);
+int himo_nsf_dt_build(const float* pc1, int n1, const float* lo, const int32_t* dims, float grid_factor,
+                      float* D, void* stream);
+int himo_nsf_optimize(const himo_nsf_desc* desc, void* stream);
 
 #ifdef __cplusplus
 }
