@@ -99,3 +99,28 @@ class SeFlowPPEngine:
             self.d2h_bytes += n_all * 12
         self.stream.synchronize()
         return host.numpy().copy()
+
+
+class FastNSFEngine:
+    """`InferenceRunner._process_step` for FastNSF (OSF/src/runner.py:130-155): ground removal, per-pair
+    optimisation, final_flow = pose_flow everywhere + optimised flow on the non-ground points."""
+
+    def __init__(self, device="cuda:0", precision: str = "fp32", seed: int = 0, **model_kw):
+        from .fastnsf import FastNSF
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.net = FastNSF(device=self.device, precision=precision, seed=seed, **model_kw)
+
+    def infer(self, frame: Dict) -> np.ndarray:
+        from .deflowpp import rigid_flow
+        pc0_all = torch.from_numpy(np.ascontiguousarray(np.asarray(frame["pc0"], np.float32)[:, :3])).to(self.device)
+        pc1_all = torch.from_numpy(np.ascontiguousarray(np.asarray(frame["pc1"], np.float32)[:, :3])).to(self.device)
+        gm0 = torch.from_numpy(np.asarray(frame.get("gm0", np.zeros(pc0_all.shape[0], bool)), bool)).to(self.device)
+        gm1 = torch.from_numpy(np.asarray(frame.get("gm1", np.zeros(pc1_all.shape[0], bool)), bool)).to(self.device)
+        batch = {"pc0": [pc0_all[~gm0].contiguous()], "pc1": [pc1_all[~gm1].contiguous()],
+                 "pose0": [torch.as_tensor(frame["pose0"])], "pose1": [torch.as_tensor(frame["pose1"])]}
+        res = self.net(batch)
+        T = cal_pose0to1(torch.as_tensor(frame["pose0"]), torch.as_tensor(frame["pose1"]))
+        final = rigid_flow(pc0_all, T)                          # pose flow for every point
+        final[~gm0] = final[~gm0] + res["flow"][0]              # runner.py:149-155
+        return final.cpu().numpy()

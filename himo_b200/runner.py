@@ -1,0 +1,183 @@
+"""Drivers behind the command lines kept from the reference: `save.py` (flow -> <res_name> in the frame
+store), `save_zip.py` (flow -> compensation-distance zip) and `eval.py` (HiMo instance metrics).
+
+Multi-GPU: one process per GPU (torchrun, or `gpus=N` which spawns them), scenes sharded round-robin
+over the ranks exactly like `SceneDistributedSampler` (OSF/src/runner.py:38-88: all frames of a scene stay
+on one rank, so no two processes ever write the same scene file); the only collective is the metric
+gather at the end (runner.py:249-256).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+
+def parse_overrides(argv: List[str], aliases: Optional[Dict[str, str]] = None) -> Dict[str, str]:
+    """Accept both spellings the reference uses: hydra `key=value` (OSF/save.py) and fire `--key value` /
+    `--key=value` (HiMo eval.py, save_zip.py)."""
+    out: Dict[str, str] = {}
+    aliases = aliases or {}
+    i = 0
+    while i < len(argv):
+        a = argv[i]
+        if a.startswith("--"):
+            a = a[2:]
+            if "=" in a:
+                k, v = a.split("=", 1)
+            elif i + 1 < len(argv) and not argv[i + 1].startswith("--"):
+                k, v = a, argv[i + 1]
+                i += 1
+            else:
+                k, v = a, "true"
+        elif "=" in a:
+            k, v = a.split("=", 1)
+        else:
+            raise SystemExit(f"cannot parse argument {a!r}")
+        k = k.replace("-", "_")
+        out[aliases.get(k, k)] = v
+        i += 1
+    return out
+
+
+def _dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard_scenes(scenes: List[str], rank: int, world: int) -> List[str]:
+    """SceneDistributedSampler (OSF/src/runner.py:74-80): sorted scenes, rank r takes scenes[r::world]."""
+    return sorted(scenes)[rank::world]
+
+
+def _build_engine(cfg: Dict[str, str], device):
+    from . import weights
+    model = cfg.get("model", "deflowpp")
+    ckpt = cfg.get("checkpoint", "")
+    if model in ("fastnsf",):
+        from .engine import FastNSFEngine
+        kw = {}
+        for k, cast in (("itr_num", int), ("early_patience", int), ("lr", float), ("min_delta", float)):
+            if k in cfg:
+                kw[k] = cast(cfg[k])
+        kw.setdefault("early_patience", 10)          # conf/model/fastnsf.yaml:13
+        return FastNSFEngine(device=device, precision=cfg.get("precision", "fp32"), **kw), 2
+    from .engine import SeFlowPPEngine
+    if ckpt.startswith("synthetic"):
+        seed = int(ckpt.split(":")[1]) if ":" in ckpt else 0
+        sd = weights.synth_deflowpp_state_dict(seed)
+    elif ckpt:
+        sd = weights.load_deflowpp_checkpoint(ckpt)
+    else:
+        raise SystemExit("save.py: checkpoint=<path to seflowpp .ckpt> (or checkpoint=synthetic:<seed>) is required")
+    return SeFlowPPEngine(sd, device=device, precision=cfg.get("precision", "fp32")), 3
+
+
+def run_save(cfg: Dict[str, str]) -> None:
+    """`python save.py checkpoint=... dataset_path=... [res_name=...]` / `python save.py model=fastnsf
+    dataset_path=...` (README.md:47-54; OSF/save.py:25-58, OSF/src/runner.py:316-343)."""
+    from .dataset import HDF5Dataset
+    rank, world, local = _dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("himo_b200 needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    data_dir = cfg.get("dataset_path") or cfg.get("data_dir")
+    if not data_dir:
+        raise SystemExit("dataset_path=<dir with index_total.pkl and scene files> is required")
+    engine, n_frames = _build_engine(cfg, dev)
+    ds = HDF5Dataset(data_dir, n_frames=n_frames)
+    res_name = cfg.get("res_name") or (cfg.get("model", "deflowpp") if "model" in cfg else "seflowpp_best")
+    mine = set(shard_scenes(list(ds.scene_id_bounds.keys()), rank, world))
+    t0, done = time.time(), 0
+    for i, (scene, ts) in enumerate(ds.data_index):
+        if scene not in mine:
+            continue
+        item = ds[i]
+        if (item["scene_id"], item["timestamp"]) != (scene, ts):
+            continue            # clamped duplicate of the neighbouring pair (last frame of a scene)
+        final = engine.infer(item)
+        ds.store.write(scene, ts, res_name, final.astype(np.float32))
+        done += 1
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(f"[save] wrote '{res_name}' for {done} frames on rank 0 of {world} in {time.time() - t0:.1f}s -> {data_dir}")
+
+
+def run_save_zip(cfg: Dict[str, str]) -> str:
+    """`python save_zip.py --data_dir ... --res_name ...` (save_zip.py:102-125)."""
+    from . import himo
+    from .dataset import HDF5Dataset
+    data_dir = cfg["data_dir"]
+    res_name = cfg.get("res_name", "seflowpp_best")
+    out_dir = os.path.join(data_dir, "results")
+    os.makedirs(out_dir, exist_ok=True)
+    ds = HDF5Dataset(data_dir, vis_name=res_name, eval=True)
+    for i in range(len(ds)):
+        data = ds[i]
+        comp = himo.comp_dis_from_total_flow(data, res_name)
+        himo.write_output_file(comp, (data["scene_id"], str(data["timestamp"])), out_dir)
+    path = himo.zip_res(out_dir, output_file=os.path.join(out_dir, f"{res_name}-submit.zip"))
+    print(f"Zipped results into {path}")
+    return path
+
+
+def run_eval(cfg: Dict[str, str]):
+    """`python eval.py --data_dir ... --res_name ... | --comp_dis_zip ...` (eval.py:270-312)."""
+    from . import himo
+    from .dataset import HDF5Dataset
+    data_dir = cfg["data_dir"]
+    res_name = cfg.get("res_name", "")
+    zip_path = cfg.get("comp_dis_zip", "")
+    data_name, flag = himo.check_valid(data_dir, res_name, zip_path)
+    rank, world, _ = _dist_env()
+    metrics = himo.InstanceMetrics(data_name)
+    ds = HDF5Dataset(data_dir, vis_name=res_name if flag == 2 else "", eval=True)
+    for i in range(rank, len(ds), world):
+        data = ds[i]
+        pc0 = data["pc0"]
+        pf = himo.pose_flow_np(pc0, data["pose0"], data["pose1"])
+        gt_flow = data["flow"] - pf
+        m = himo.eval_masks(data, data_name)
+        dt0 = max(data["lidar_dt"]) - data["lidar_dt"]
+        if flag == 2:
+            est = np.zeros_like(pf) if res_name == "raw" else (data[res_name] - pf)
+            metrics.step_eval(pc0[m], gt_flow[m], dt0[m], data["flow_category_indices"][m],
+                              data["flow_instance_id"][m], est_flow=est[m])
+        else:
+            comp = himo.read_output_zip(zip_path, (data["scene_id"], str(data["timestamp"])))
+            metrics.step_eval(pc0[m], gt_flow[m], dt0[m], data["flow_category_indices"][m],
+                              data["flow_instance_id"][m], est_dis=comp[m])
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(metrics, gathered, dst=0)
+        if rank == 0:
+            for other in gathered[1:]:
+                metrics.merge(other)
+        dist.barrier()
+    if rank == 0:
+        return metrics.print(res_name=res_name or "zip", file_name=cfg.get("out_json", f"res-{data_name}.json"))
+    return None
+
+
+def main_save(argv=None):
+    run_save(parse_overrides(sys.argv[1:] if argv is None else argv))
+
+
+def main_save_zip(argv=None):
+    run_save_zip(parse_overrides(sys.argv[1:] if argv is None else argv))
+
+
+def main_eval(argv=None):
+    run_eval(parse_overrides(sys.argv[1:] if argv is None else argv, aliases={"flow_mode": "res_name"}))

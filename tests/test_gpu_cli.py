@@ -1,0 +1,70 @@
+"""GPU: the kept command lines end to end on a synthetic AV2-shaped dataset:
+save.py (SeFlow++ and FastNSF) -> <res_name> in the frame store -> save_zip.py -> eval.py (flow and zip)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from himo_b200 import himo, store, weights
+from himo_b200.dataset import HDF5Dataset
+from oracle import deflowpp_ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def data_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cli_av2_synth")
+    store.write_synthetic_dataset(str(d), n_scenes=2, n_frames=5, n_points=3000, seed=5)
+    return str(d)
+
+
+def _run(args):
+    r = subprocess.run([sys.executable] + args, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_save_seflowpp_then_zip_then_eval(data_dir):
+    _run(["save.py", "checkpoint=synthetic:4", f"dataset_path={data_dir}", "res_name=seflowpp_synth"])
+    ds = HDF5Dataset(data_dir, n_frames=3, vis_name="seflowpp_synth")
+    item = ds[2]
+    got = item["seflowpp_synth"]
+    assert got.shape == item["pc0"].shape and got.dtype == np.float32
+    # the stored array is what ModelWrapper.test_step writes: check it against the CPU oracle
+    sd = weights.synth_deflowpp_state_dict(4)
+    ng = lambda pc, gm: pc[~gm]
+    res = deflowpp_ref.deflowpp_forward(sd, ng(item["pch1"], item["gmh1"]), ng(item["pc0"], item["gm0"]),
+                                        ng(item["pc1"], item["gm1"]), item["poseh1"], item["pose0"], item["pose1"])
+    ref = deflowpp_ref.final_flow(torch.from_numpy(item["pc0"]), torch.from_numpy(item["gm0"]), item["pose0"],
+                                  item["pose1"], res).numpy()
+    assert np.abs(got - ref).max() <= 1e-4
+    out = _run(["save_zip.py", "--data_dir", data_dir, "--res_name", "seflowpp_synth"])
+    z = os.path.join(data_dir, "results", "seflowpp_synth-submit.zip")
+    assert os.path.exists(z), out
+    j1 = os.path.join(data_dir, "flow.json")
+    j2 = os.path.join(data_dir, "zip.json")
+    _run(["eval.py", "--data_dir", data_dir, "--res_name", "seflowpp_synth", "--out_json", j1])
+    _run(["eval.py", "--data_dir", data_dir, "--flow_mode", "seflowpp_synth", "--comp_dis_zip", z, "--out_json", j2])
+    a = json.load(open(j1))["av2"]["seflowpp_synth"]
+    b = json.load(open(j2))["av2"]["seflowpp_synth"]
+    assert a.keys() == b.keys() and len(a) > 0
+    for c in a:   # the zip carries float32 compensation distances: same metrics up to that rounding
+        assert abs(a[c]["overall"]["mpe"] - b[c]["overall"]["mpe"]) < 1e-5
+
+
+def test_save_fastnsf_plumbing(data_dir):
+    """BASELINE configs[0]: FastNSF through the save.py command line (few iterations: plumbing)."""
+    _run(["save.py", "model=fastnsf", f"dataset_path={data_dir}", "itr_num=6", "res_name=fastnsf"])
+    ds = HDF5Dataset(data_dir, vis_name="fastnsf")
+    item = ds[1]
+    f = item["fastnsf"]
+    assert f.shape == item["pc0"].shape and np.isfinite(f).all()
+    pf = himo.pose_flow_np(item["pc0"], item["pose0"], item["pose1"])
+    # ground points carry the ego-motion flow only (OSF/src/runner.py:149-155)
+    np.testing.assert_allclose(f[item["gm0"]], pf[item["gm0"]], rtol=0, atol=1e-4)

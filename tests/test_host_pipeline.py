@@ -1,0 +1,133 @@
+"""CPU: host logic around the path -- frame store, HDF5Dataset work-alike, HiMo compensation / metrics
+against the reference's own Python (utils/__init__.py, tools/test/score.py) when /root/reference is
+present, CLI argument parsing, scene sharding, and the world_size-2 gloo metric gather."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from himo_b200 import himo, runner, store
+from himo_b200.dataset import HDF5Dataset
+
+REF = "/root/reference"
+
+
+@pytest.fixture(scope="module")
+def dataset_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("himo_av2_synth")
+    store.write_synthetic_dataset(str(d), n_scenes=2, n_frames=5, n_points=2500, seed=3)
+    return str(d)
+
+
+def test_store_roundtrip_and_replace(tmp_path):
+    st = store.NpyStore(str(tmp_path))
+    a = np.arange(12, dtype=np.float32).reshape(4, 3)
+    st.write("s", "100", "flow", a)
+    st.write("s", "100", "flow", a + 1)             # del + create semantics: re-runs replace
+    assert (st.read("s", "100", "flow") == a + 1).all() and st.has("s", "100", "flow")
+    assert st.scenes() == ["s"] and st.names("s", "100") == ["flow"]
+
+
+def test_dataset_pair_assembly(dataset_dir):
+    ds = HDF5Dataset(dataset_dir, n_frames=3)
+    assert len(ds) == 10
+    first, last = ds[0], ds[4]
+    # history clamps at the scene start; the last frame of a scene is served by the previous pair
+    assert first["timestamp"] == ds.data_index[1][1] or first["timestamp"] == ds.data_index[0][1]
+    assert last["timestamp"] == ds.data_index[3][1]
+    it = ds[2]
+    assert it["pc0"].shape[1] == 3 and it["gm0"].dtype == bool and it["pose0"].shape == (4, 4)
+    assert (it["pose1"] == ds.store.read(it["scene_id"], ds.data_index[3][1], "pose")).all()
+    assert (it["poseh1"] == ds.store.read(it["scene_id"], ds.data_index[1][1], "pose")).all()
+    ev = HDF5Dataset(dataset_dir, eval=True)
+    assert len(ev) == 2 and ev[0]["eval_flag"] and "eval_mask" in ev[0] and "lidar_dt" in ev[0]
+
+
+def test_parse_overrides_and_sharding():
+    cfg = runner.parse_overrides(["checkpoint=a.ckpt", "dataset_path=/d", "--res_name", "x", "--flow-mode=y"],
+                                 aliases={"flow_mode": "res_name2"})
+    assert cfg == {"checkpoint": "a.ckpt", "dataset_path": "/d", "res_name": "x", "res_name2": "y"}
+    scenes = [f"s{i}" for i in range(13)]
+    parts = [runner.shard_scenes(scenes, r, 8) for r in range(8)]
+    assert sorted(sum(parts, [])) == sorted(scenes) and [len(p) for p in parts] == [2, 2, 2, 2, 2, 1, 1, 1]
+
+
+def test_compdis_and_zip_roundtrip(dataset_dir, tmp_path):
+    ds = HDF5Dataset(dataset_dir, eval=True)
+    data = ds[0]
+    data["gt"] = data["flow"]
+    comp = himo.comp_dis_from_total_flow(data, "gt")
+    dt0 = data["lidar_dt"].max() - data["lidar_dt"]
+    pf = himo.pose_flow_np(data["pc0"], data["pose0"], data["pose1"])
+    np.testing.assert_allclose(comp, (data["flow"] - pf) / 0.1 * dt0[:, None], rtol=1e-6, atol=1e-7)
+    himo.write_output_file(comp, (data["scene_id"], str(data["timestamp"])), tmp_path / "results")
+    z = himo.zip_res(tmp_path / "results", str(tmp_path / "x-submit.zip"))
+    back = himo.read_output_zip(z, (data["scene_id"], str(data["timestamp"])))
+    assert back.dtype == np.float32 and (back == comp.astype(np.float32)).all()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs /root/reference")
+def test_against_reference_utils_and_scorer(dataset_dir):
+    """flow2compDis / ego_pts_mask against HiMo's own utils, and InstanceMetrics against the reference's
+    stand-alone scorer (tools/test/score.py, 'matching eval.py exactly')."""
+    sys.path.insert(0, REF)
+    import importlib
+    ref_utils = importlib.import_module("utils")
+    spec = importlib.util.spec_from_file_location("himo_ref_score", os.path.join(REF, "tools", "test", "score.py"))
+    score = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(score)
+    sys.path.remove(REF)
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-12, 12, (5000, 3)).astype(np.float32)
+    assert (himo.ego_pts_mask(pts) == ref_utils.ego_pts_mask(pts)).all()
+    fl = rng.normal(size=(5000, 3)).astype(np.float32)
+    dt = rng.uniform(0, 0.1, 5000).astype(np.float32)
+    assert (himo.flow2compDis(fl, dt, 0.1) == ref_utils.flow2compDis(fl, dt, 0.1)).all()
+    assert himo.CATEGORY_TO_INDEX == score.CATEGORY_TO_INDEX
+    ours, ref = himo.InstanceMetrics("av2"), score.ScoreMetrics()
+    ds = HDF5Dataset(dataset_dir, eval=True)
+    for i in range(len(ds)):
+        d = ds[i]
+        pf = himo.pose_flow_np(d["pc0"], d["pose0"], d["pose1"])
+        gt = d["flow"] - pf
+        est = gt + rng.normal(0, 0.05, gt.shape).astype(np.float32)
+        m = himo.eval_masks(d, "av2")
+        dt0 = d["lidar_dt"].max() - d["lidar_dt"]
+        ours.step_eval(d["pc0"][m], gt[m], dt0[m], d["flow_category_indices"][m], d["flow_instance_id"][m], est_flow=est[m])
+        ref.step(himo.flow2compDis(gt, dt0, 0.1), himo.flow2compDis(est, dt0, 0.1), m, d["flow_category_indices"],
+                 d["flow_instance_id"].astype(np.uint32), np.linalg.norm(gt, axis=1), d["pc0"])
+    s, r = ours.summary(), ref.compute_scores()
+    assert "CAR" in s or "OTHER_VEHICLES" in s, "synthetic world produced no moving instances"
+    for c, key in (("CAR", "car"), ("OTHER_VEHICLES", "others")):
+        if c in s:
+            assert abs(s[c]["overall"]["mpe"] - r[f"{key}_mpe"]) < 1e-6
+            assert abs(s[c]["overall"]["cd"] - r[f"{key}_cde"]) < 1e-6
+            assert s[c]["overall"]["num_pts"] == r[f"{key}_num_pts"]
+    assert abs(s["Total"]["mpe"] - r["mpe"]) < 1e-6 and abs(s["Total"]["cd"] - r["chamfer"]) < 1e-6
+
+
+def _gather_worker(rank, world, port, data_dir, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = runner.run_eval({"data_dir": data_dir, "res_name": "flow", "out_json": out})
+    dist.destroy_process_group()
+    if rank == 0:
+        assert res is not None
+
+
+def test_eval_two_ranks_matches_one(dataset_dir, tmp_path):
+    """world_size-2 gloo run of the eval driver: the merged metrics equal the single-process ones."""
+    import json
+    import torch.multiprocessing as mp
+    d = dataset_dir  # name contains 'av2'
+    one = runner.run_eval({"data_dir": d, "res_name": "flow", "out_json": str(tmp_path / "one.json")})
+    mp.spawn(_gather_worker, args=(2, 29613, d, str(tmp_path / "two.json")), nprocs=2, join=True)
+    a = json.load(open(tmp_path / "one.json"))["av2"]["flow"]
+    b = json.load(open(tmp_path / "two.json"))["av2"]["flow"]
+    assert a.keys() == b.keys() and len(a) > 0
+    for c in a:
+        assert a[c]["overall"]["num_pts"] == b[c]["overall"]["num_pts"]
+        assert abs(a[c]["overall"]["mpe"] - b[c]["overall"]["mpe"]) < 1e-9
