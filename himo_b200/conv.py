@@ -25,6 +25,8 @@ class ConvDesc(ctypes.Structure):
         ("mask_src", c_void_p), ("mask_plane_stride", c_longlong), ("mask_planes", c_int),
         ("b_group_k_stride", c_int), ("out_group_pix_stride", c_longlong), ("b_k_total", c_longlong),
         ("stop_flag", c_void_p),
+        ("aux_h", c_void_p), ("aux_z", c_void_p), ("aux_ld", c_int),
+        ("out2", c_void_p), ("out2_plane_stride", c_longlong), ("out2_ld", c_int),
     ]
 
 

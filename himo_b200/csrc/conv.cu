@@ -29,11 +29,13 @@
 namespace himo {
 
 constexpr int kConvBM = 128;
+constexpr int kConvBK = 32;               // input channels per pipeline stage (64-byte swizzled rows)
+constexpr int kConvRowB = 64;
 constexpr int kConvEpiWarps = 8;
 constexpr int kConvThreads = 64 + kConvEpiWarps * 32;
 
 struct ConvParams {
-  int tiles_x, tiles_y, n_tiles_n, n_groups;
+  int tiles_x, tiles_y, n_tiles_n, n_groups, total_tiles;
   int TW, TH;
   int taps, ksize, pad, stride;
   int Cin, cin_off, cin_group_stride, k_chunks;
@@ -44,7 +46,7 @@ struct ConvParams {
   int W_out, Cout_total, cout_off, cout_group_stride;
   int act, out_fp32;
   float acc_scale;
-  int flush_iters;
+  int flush_stages;
   // GEMM-epilogue extensions used by the FastNSF MLP (csrc/nsf.cu)
   __nv_bfloat16* out_t;            // optional transposed copy: [planes][Cout_total][ld_t], column = pixel
   long long out_t_plane_stride;
@@ -55,64 +57,214 @@ struct ConvParams {
   int b_group_k_stride;            // split-K: K offset of the B operand per group
   long long out_group_pix_stride;  // split-K: output row offset per group
   const int* stop_flag;            // optional device flag: non-zero => the whole launch is a no-op
+  // fused ConvGRU epilogues (act 5 / 6), see the epilogue
+  float* aux_h;                    // [pixels][aux_ld] fp32 hidden state h
+  float* aux_z;                    // [pixels][aux_ld] fp32 update gate z
+  int aux_ld;
+  __nv_bfloat16* out2;             // split-plane operand buffer of the NEXT GEMM ([planes][pixels][out2_ld])
+  long long out2_plane_stride;
+  int out2_ld;
 };
 
 __device__ __forceinline__ float gelu_erf(float v) {
   return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
 }
 
-template <int BN, int BK, int P, int STAGES>
-struct ConvSmem {
-  static constexpr int kABytes = kConvBM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = P * (kABytes + kBBytes);
+// Pipeline stage = one A load shared by NX taps + the NX weight tiles.
+//   NX == 3 ("halo" mode, 3x3 stride-1 convs on rows >= 128 px): the A tile is ONE haloed row of
+//     128+2 pixels x 32 channels; the taps kx = 0,1,2 read it through three descriptors whose start
+//     address is shifted by one 64-byte row each (the tensor core swizzles on absolute shared-memory
+//     address bits, like TMA -- profiles/r01_exp_shifted_descriptor.txt), so the activation tile is
+//     fetched from L2 three times per output tile instead of nine.
+//   NX == 1: one tap per stage (1x1 convs, stride-2 convs, 64-px rows, plain GEMMs).
+// CG == 2: a pair of CTAs (thread-block cluster of 2) computes a 256-pixel x BN tile with
+// tcgen05.mma.cta_group::2: each CTA stages its own 128 pixels of A and only HALF of the weight rows, the
+// leader CTA issues the MMAs for both, and every weight byte is fetched from L2 once per 256 pixels.
+template <int BN, int P, int NX, int CG>
+struct ConvCfg {
+  static constexpr int kARows = NX == 3 ? 136 : 128;                 // smem rows reserved per A plane
+  static constexpr int kARowsTx = NX == 3 ? 130 : 128;               // rows TMA really writes
+  static constexpr int kABytes = kARows * kConvRowB;
+  static constexpr int kBRows = BN / CG;                             // weight rows staged by this CTA
+  static constexpr int kBBytes = kBRows * kConvRowB;
+  static constexpr int kStageBytes = P * kABytes + NX * P * kBBytes;
+  static constexpr int kTxBytes = P * kARowsTx * kConvRowB + NX * P * kBBytes;
+  static constexpr int kStagesRaw = (224 * 1024 - 1024) / kStageBytes;
+  static constexpr int STAGES = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 256 + BN * 4 + 1024;  // + barriers + bias + align slack
+  static constexpr int kTotal = kBarOffset + 512 + 128;              // barriers + alignment slack
+  static constexpr int kUsedCols = P == 2 ? 3 * BN : 2 * BN;
+  static constexpr int kTmemCols = kUsedCols <= 64 ? 64 : kUsedCols <= 128 ? 128 : kUsedCols <= 256 ? 256 : 512;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
-// Accumulation scheme (split mode, P == 2).  tcgen05 adds every MMA into the fp32 TMEM accumulator
-// with truncation, so a long accumulation chain drifts by ~0.5 ulp per MMA (measured: error grows
-// linearly with K).  To stay fp32-class:
-//   * the small cross products hi*lo + lo*hi go to their own accumulator ("cross"), so they never
+// Tile epilogue for one thread: kHalfT accumulator columns of one output pixel.
+template <int ACT, int kHalfT>
+__device__ __forceinline__ void conv_epilogue(const float* acc, const ConvParams& p, long long pix, long long ch0,
+                                              const float* bias) {
+#pragma unroll
+for (int gi = 0; gi < kHalfT / 16; ++gi) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float x = __fmaf_rn(acc[gi * 16 + j], p.acc_scale, bias ? __ldg(bias + gi * 16 + j) : 0.f);
+    if (ACT == 1) v[j] = gelu_erf(x);
+    else if (ACT == 2) v[j] = __fdiv_rn(1.0f, 1.0f + expf(-x));     // torch.sigmoid
+    else if (ACT == 3) v[j] = tanhf(x);                              // torch.tanh
+    else if (ACT == 4) v[j] = fmaxf(x, 0.f);                         // ReLU
+    else v[j] = x;                                                   // 0: none; 5/6: fused ConvGRU below
+  }
+  if (p.mask_src) {   // ReLU backward: pass the gradient where the forward activation was > 0
+    const __nv_bfloat16* m = p.mask_src + pix * p.Cout_total + ch0 + gi * 16;
+    uint32_t mb[8];
+    *(uint4*)&mb[0] = *(const uint4*)m;
+    *(uint4*)&mb[4] = *(const uint4*)(m + 8);
+    if (p.mask_planes == 2) {
+      uint32_t m2[8];
+      *(uint4*)&m2[0] = *(const uint4*)(m + p.mask_plane_stride);
+      *(uint4*)&m2[4] = *(const uint4*)(m + p.mask_plane_stride + 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mb[j] |= m2[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if ((mb[j] & 0x00007fffu) == 0u) v[2 * j] = 0.f;
+      if ((mb[j] & 0x7fff0000u) == 0u) v[2 * j + 1] = 0.f;
+    }
+  }
+  if (p.out_t) {      // transposed split-plane copy: element (channel, pixel); lanes = consecutive pixels
+    const bool split_t = p.out_planes == 2;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      umma::store_split(p.out_t + (ch0 + gi * 16 + j) * (long long)p.ld_t + pix, p.out_t_plane_stride,
+                        split_t ? 2 : 1, v[j]);
+  }
+  if (ACT >= 5) {
+    // ConvGRU fused epilogues (OSF/src/models/basic/decoder.py:185-192), column c of this GEMM:
+    //  act 5 (zr GEMM, 2*aux_ld columns): c <  aux_ld: z = sigmoid(.) -> aux_z
+    //                                     c >= aux_ld: r = sigmoid(.), out2[:, c-aux_ld] = split(r*h)
+    //  act 6 (q GEMM): q = tanh(.), h <- (1-z)*h + z*q -> aux_h and out2[:, c] = split(h)
+    const long long cbase = ch0 + gi * 16;
+    const bool split2 = p.out_planes == 2;
+    if (ACT == 5) {
+      if (cbase < p.aux_ld) {
+        float4* zp = (float4*)(p.aux_z + pix * p.aux_ld + cbase);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 t;
+          t.x = __fdiv_rn(1.0f, 1.0f + expf(-v[4 * j])); t.y = __fdiv_rn(1.0f, 1.0f + expf(-v[4 * j + 1]));
+          t.z = __fdiv_rn(1.0f, 1.0f + expf(-v[4 * j + 2])); t.w = __fdiv_rn(1.0f, 1.0f + expf(-v[4 * j + 3]));
+          zp[j] = t;
+        }
+      } else {
+        const long long c2 = cbase - p.aux_ld;
+        const float4* hp = (const float4*)(p.aux_h + pix * p.aux_ld + c2);
+        float rh[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 h4 = hp[j];
+          rh[4 * j] = __fdiv_rn(1.0f, 1.0f + expf(-v[4 * j])) * h4.x;
+          rh[4 * j + 1] = __fdiv_rn(1.0f, 1.0f + expf(-v[4 * j + 1])) * h4.y;
+          rh[4 * j + 2] = __fdiv_rn(1.0f, 1.0f + expf(-v[4 * j + 2])) * h4.z;
+          rh[4 * j + 3] = __fdiv_rn(1.0f, 1.0f + expf(-v[4 * j + 3])) * h4.w;
+        }
+        __nv_bfloat16* o2 = p.out2 + pix * p.out2_ld + c2;
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) umma::pack_split2(rh[2 * j], rh[2 * j + 1], split2, hi[j], lo[j]);
+        ((uint4*)o2)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        ((uint4*)o2)[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        if (split2) {
+          ((uint4*)(o2 + p.out2_plane_stride))[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          ((uint4*)(o2 + p.out2_plane_stride))[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
+      }
+    } else {
+      float4* hp = (float4*)(p.aux_h + pix * p.aux_ld + cbase);
+      const float4* zp = (const float4*)(p.aux_z + pix * p.aux_ld + cbase);
+      float hn[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 h4 = hp[j], z4 = zp[j];
+        hn[4 * j] = __fadd_rn(__fmul_rn(1.0f - z4.x, h4.x), __fmul_rn(z4.x, tanhf(v[4 * j])));
+        hn[4 * j + 1] = __fadd_rn(__fmul_rn(1.0f - z4.y, h4.y), __fmul_rn(z4.y, tanhf(v[4 * j + 1])));
+        hn[4 * j + 2] = __fadd_rn(__fmul_rn(1.0f - z4.z, h4.z), __fmul_rn(z4.z, tanhf(v[4 * j + 2])));
+        hn[4 * j + 3] = __fadd_rn(__fmul_rn(1.0f - z4.w, h4.w), __fmul_rn(z4.w, tanhf(v[4 * j + 3])));
+        hp[j] = make_float4(hn[4 * j], hn[4 * j + 1], hn[4 * j + 2], hn[4 * j + 3]);
+      }
+      __nv_bfloat16* o2 = p.out2 + pix * p.out2_ld + cbase;
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) umma::pack_split2(hn[2 * j], hn[2 * j + 1], split2, hi[j], lo[j]);
+      ((uint4*)o2)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      ((uint4*)o2)[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+      if (split2) {
+        ((uint4*)(o2 + p.out2_plane_stride))[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        ((uint4*)(o2 + p.out2_plane_stride))[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      }
+    }
+    continue;
+  }
+  if (p.out_fp32) {
+    float4* dst = (float4*)((float*)p.out + pix * p.Cout_total + ch0 + gi * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+    __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * p.Cout_total + ch0 + gi * 16;
+    const bool split = p.out_planes == 2;
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) umma::pack_split2(v[2 * j], v[2 * j + 1], split, hi[j], lo[j]);
+    uint4* dst = (uint4*)o;
+    dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    if (split) {
+      uint4* dst2 = (uint4*)(o + p.out_plane_stride);
+      dst2[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      dst2[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    }
+  }
+}
+}
+
+// Accumulation scheme.  tcgen05 adds every MMA into the fp32 TMEM accumulator with truncation, so a long
+// accumulation chain drifts by ~0.5 ulp per MMA (measured: error grows linearly with K).  To stay fp32-class
+//   * split mode: the small cross products hi*lo + lo*hi go to their own accumulator ("cross") and never
 //     round the large hi*hi sum;
-//   * the hi*hi chain is cut every `flush_iters` k-iterations: the MMA warp ping-pongs between two
-//     "main" accumulators and the epilogue warps drain the finished one into fp32 registers
-//     (round-to-nearest adds) while the tensor core fills the other.
-// TMEM columns: main0 [0,BN), main1 [BN,2BN), cross [2BN,3BN).  Single-plane mode uses main0 only.
-template <int BN, int BK, int P, int STAGES>
-__global__ void __launch_bounds__(kConvThreads)
+//   * the hi*hi chain is cut every `flush_stages` stages: the MMA warp ping-pongs between two "main"
+//     accumulators and the epilogue warps drain the finished one into fp32 registers (round-to-nearest)
+//     while the tensor core fills the other.
+// TMEM columns: main0 [0,BN), main1 [BN,2BN), cross [2BN,3BN).
+// The kernel is persistent: one CTA per SM walks the tile list, barrier phases run across tiles, and the
+// store epilogue of tile i overlaps the main loop of tile i+1.
+template <int BN, int P, int NX, int CG>
+__global__ void __launch_bounds__(kConvThreads, 1)
 k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const ConvParams p) {
-  using S = ConvSmem<BN, BK, P, STAGES>;
-  constexpr int kUsedCols = P == 2 ? 3 * BN : BN;
-  constexpr int kTmemCols = kUsedCols <= 32 ? 32 : kUsedCols <= 64 ? 64 : kUsedCols <= 128 ? 128
-                            : kUsedCols <= 256 ? 256 : 512;
-  constexpr int kRowBytes = BK * 2;
+  using C = ConvCfg<BN, P, NX, CG>;
+  constexpr int STAGES = C::STAGES;
   constexpr int kHalf = BN / 2;            // columns owned by one epilogue thread
   constexpr int kGroups = kHalf / 16;
   static_assert(kHalf % 16 == 0, "BN must be a multiple of 32");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + S::kBarOffset);
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  uint64_t* full_bar = (uint64_t*)(smem + C::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full_bar = empty_bar + STAGES;     // [2]
   uint64_t* acc_empty_bar = acc_full_bar + 2;      // [2]
-  uint32_t* tmem_ptr_smem = (uint32_t*)(acc_empty_bar + 2);
-  float* bias_s = (float*)(smem + S::kBarOffset + 256);
+  uint64_t* cross_empty_bar = acc_empty_bar + 2;   // [1]
+  uint32_t* tmem_ptr_smem = (uint32_t*)(cross_empty_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.stop_flag && *p.stop_flag) return;   // uniform across the grid
+  const uint32_t cta_rank = CG == 2 ? umma::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int n_workers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;    // CTAs (or CTA pairs)
+  const int worker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
 
-  // tile decode: n-tile fastest so CTAs that share an A tile are co-scheduled (L2 reuse)
-  int t = blockIdx.x;
-  const int nt = t % p.n_tiles_n; t /= p.n_tiles_n;
-  const int tx = t % p.tiles_x; t /= p.tiles_x;
-  const int ty = t % p.tiles_y; t /= p.tiles_y;
-  const int g = t;
-  const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BN;
-  const int k_iters = p.taps * p.k_chunks;
-  const int flush = P == 2 ? p.flush_iters : k_iters;
+  const int k_iters = (p.taps / NX) * p.k_chunks;          // pipeline stages per tile
+  const int flush = P == 2 ? p.flush_stages : k_iters;
   const int n_chunks = (k_iters + flush - 1) / flush;
 
   if (warp == 0 && lane == 0) {
@@ -124,84 +276,148 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int b = 0; b < 2; ++b) {
       umma::mbar_init(&acc_full_bar[b], 1);
-      umma::mbar_init(&acc_empty_bar[b], kConvEpiWarps);
+      umma::mbar_init(&acc_empty_bar[b], kConvEpiWarps * CG);    // CG == 2: both CTAs' epilogues report to the leader
     }
+    umma::mbar_init(cross_empty_bar, kConvEpiWarps * CG);
     umma::fence_barrier_init();
   } else if (warp == 1) {
-    umma::tmem_alloc(tmem_ptr_smem, kTmemCols);
-  } else if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += kConvEpiWarps * 32) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+    if (CG == 2) umma::tmem_alloc_2cta(tmem_ptr_smem, C::kTmemCols);
+    else umma::tmem_alloc(tmem_ptr_smem, C::kTmemCols);
   }
   umma::tc_fence_before();
   __syncthreads();
+  if (CG == 2) umma::cluster_sync();       // peer barriers are initialised before anything signals them
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // tile decode: n-tile fastest so CTAs that run concurrently share A tiles in L2
+  // (for CG == 2 `t` indexes pairs of M tiles; this CTA takes M tile 2*pair + rank)
+  auto decode = [&](int t, int& g, int& x0, int& y0, int& n0) {
+    const int nt = t % p.n_tiles_n; t /= p.n_tiles_n;
+    const int m_tiles = p.tiles_x * p.tiles_y;
+    int m = CG == 2 ? (t % (m_tiles >> 1)) * 2 + (int)cta_rank : t % m_tiles;
+    g = CG == 2 ? t / (m_tiles >> 1) : t / m_tiles;
+    const int tx = m % p.tiles_x, ty = m / p.tiles_x;
+    x0 = tx * p.TW; y0 = ty * p.TH; n0 = nt * BN;
+  };
+  const int total_work = CG == 2 ? p.total_tiles >> 1 : p.total_tiles;
+
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      const int cin0 = p.cin_off + g * p.cin_group_stride;
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        umma::mbar_wait(&empty_bar[s], ph ^ 1);
-        umma::mbar_arrive_expect_tx(&full_bar[s], S::kStageBytes);
-        const int tap = it / p.k_chunks, kc = it - tap * p.k_chunks;
-        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-        uint8_t* a_dst = smem + s * S::kStageBytes;
-        uint8_t* b_dst = a_dst + P * S::kABytes;
+    {
+      // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+      uint32_t git = 0;
+      for (int tile = worker; tile < total_work; tile += n_workers) {
+        int g, x0, y0, n0;
+        decode(tile, g, x0, y0, n0);
+        const int cin0 = p.cin_off + g * p.cin_group_stride;
+        const int bk0 = g * p.b_group_k_stride;
+        const int nb0 = n0 + (int)cta_rank * C::kBRows;      // this CTA's share of the weight rows
+        for (int it = 0; it < k_iters; ++it, ++git) {
+          const int s = git % STAGES;
+          const uint32_t ph = (git / STAGES) & 1;
+          umma::mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t fb = CG == 2 ? umma::mapa_u32(umma::smem_u32(&full_bar[s]), 0) : 0u;
+          uint8_t* a_dst = smem + s * C::kStageBytes;
+          uint8_t* b_dst = a_dst + P * C::kABytes;
+          if (!umma::elect_one()) continue;
+          // CG == 2: both CTAs' bytes are counted on the LEADER's full barrier
+          if (leader) umma::mbar_arrive_expect_tx(&full_bar[s], C::kTxBytes * CG);
+          if (NX == 3) {
+            const int kc = it / 3, ky = it - kc * 3;       // channel chunk outer, kernel row inner
 #pragma unroll
-        for (int pl = 0; pl < P; ++pl)
-          umma::tma_load_4d(a_dst + pl * S::kABytes, &tmA, &full_bar[s], cin0 + kc * BK,
-                            x0 * p.stride + kx - p.pad, y0 * p.stride + ky - p.pad, pl);
+            for (int pl = 0; pl < P; ++pl) {
+              if (CG == 2) umma::tma_load_4d_2cta(a_dst + pl * C::kABytes, &tmA, fb, cin0 + kc * kConvBK, x0 - 1, y0 + ky - 1, pl);
+              else umma::tma_load_4d(a_dst + pl * C::kABytes, &tmA, &full_bar[s], cin0 + kc * kConvBK, x0 - 1, y0 + ky - 1, pl);
+            }
 #pragma unroll
-        for (int pl = 0; pl < P; ++pl)
-          umma::tma_load_3d(b_dst + pl * S::kBBytes, &tmB, &full_bar[s],
-                            g * p.b_group_k_stride + tap * p.Cin + kc * BK, n0, pl);
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+              for (int pl = 0; pl < P; ++pl) {
+                const int kk = bk0 + (ky * 3 + kx) * p.Cin + kc * kConvBK;
+                if (CG == 2) umma::tma_load_3d_2cta(b_dst + (kx * P + pl) * C::kBBytes, &tmB, fb, kk, nb0, pl);
+                else umma::tma_load_3d(b_dst + (kx * P + pl) * C::kBBytes, &tmB, &full_bar[s], kk, nb0, pl);
+              }
+          } else {
+            const int tap = it / p.k_chunks, kc = it - tap * p.k_chunks;
+            const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+#pragma unroll
+            for (int pl = 0; pl < P; ++pl) {
+              if (CG == 2) umma::tma_load_4d_2cta(a_dst + pl * C::kABytes, &tmA, fb, cin0 + kc * kConvBK,
+                                                  x0 * p.stride + kx - p.pad, y0 * p.stride + ky - p.pad, pl);
+              else umma::tma_load_4d(a_dst + pl * C::kABytes, &tmA, &full_bar[s], cin0 + kc * kConvBK,
+                                     x0 * p.stride + kx - p.pad, y0 * p.stride + ky - p.pad, pl);
+            }
+#pragma unroll
+            for (int pl = 0; pl < P; ++pl) {
+              const int kk = bk0 + tap * p.Cin + kc * kConvBK;
+              if (CG == 2) umma::tma_load_3d_2cta(b_dst + pl * C::kBBytes, &tmB, fb, kk, nb0, pl);
+              else umma::tma_load_3d(b_dst + pl * C::kBBytes, &tmB, &full_bar[s], kk, nb0, pl);
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    if (leader) {
+      // ===================== MMA issuer (leader CTA only when CG == 2) =====================
+      // the whole warp runs the loop; tcgen05.mma / commit are issued by one elected lane
       // kind::f16 format codes: 0 = fp16 (split mode, both planes), 1 = bf16 (single-plane mode)
       constexpr uint32_t kFmt = P == 2 ? 0u : 1u;
-      constexpr uint32_t idesc = umma::idesc_f16kind_f32(kConvBM, BN, kFmt, kFmt);
+      constexpr uint32_t idesc = umma::idesc_f16kind_f32(kConvBM * CG, BN, kFmt, kFmt);
       const uint32_t tmem_cross = tmem_base + 2 * BN;
-      int it = 0;
-      for (int chunk = 0; chunk < n_chunks; ++chunk) {
-        const int buf = chunk & 1;
-        const uint32_t tmem_main = tmem_base + buf * BN;
-        if (P == 2) {   // wait until the epilogue has drained this accumulator (2 chunks ago)
-          umma::mbar_wait(&acc_empty_bar[buf], ((chunk >> 1) & 1) ^ 1);
+      auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if (CG == 2) umma::mma_bf16_ss_2cta(d, a, b, id, acc);
+        else umma::mma_bf16_ss(d, a, b, id, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if (CG == 2) umma::mma_commit_2cta(bar);
+        else umma::mma_commit(bar);
+      };
+      uint32_t git = 0, gch = 0, tcount = 0;
+      for (int tile = worker; tile < total_work; tile += n_workers, ++tcount) {
+        if (P == 2) {   // the epilogue must have read the previous tile's cross accumulator
+          umma::mbar_wait(cross_empty_bar, (tcount & 1) ^ 1);
           umma::tc_fence_after();
         }
-        const int it_begin = it, it_end = min(it + flush, k_iters);
-        for (; it < it_end; ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          umma::mbar_wait(&full_bar[s], ph);
+        int it = 0;
+        for (int chunk = 0; chunk < n_chunks; ++chunk, ++gch) {
+          const int buf = gch & 1;
+          const uint32_t tmem_main = tmem_base + buf * BN;
+          umma::mbar_wait(&acc_empty_bar[buf], ((gch >> 1) & 1) ^ 1);   // drained two chunks ago
           umma::tc_fence_after();
-          const uint32_t a_addr = umma::smem_u32(smem + s * S::kStageBytes);
-          const uint32_t b_addr = a_addr + P * S::kABytes;
-          uint64_t adesc[P], bdesc[P];
+          const int it_begin = it, it_end = min(it + flush, k_iters);
+          for (; it < it_end; ++it, ++git) {
+            const int s = git % STAGES;
+            const uint32_t ph = (git / STAGES) & 1;
+            umma::mbar_wait(&full_bar[s], ph);
+            umma::tc_fence_after();
+            const uint32_t a_addr = umma::smem_u32(smem + s * C::kStageBytes);
+            const uint32_t b_addr = a_addr + P * C::kABytes;
+            if (umma::elect_one()) {
 #pragma unroll
-          for (int pl = 0; pl < P; ++pl) {
-            adesc[pl] = umma::smem_desc_kmajor<kRowBytes>(a_addr + pl * S::kABytes);
-            bdesc[pl] = umma::smem_desc_kmajor<kRowBytes>(b_addr + pl * S::kBBytes);
-          }
+            for (int kx = 0; kx < NX; ++kx) {
+              // halo mode: tap kx reads rows [kx, kx+128) of the haloed A tile
+              const uint64_t a_hi = umma::smem_desc_kmajor<kConvRowB>(a_addr + kx * kConvRowB);
+              const uint64_t a_lo = umma::smem_desc_kmajor<kConvRowB>(a_addr + (P - 1) * C::kABytes + kx * kConvRowB);
+              const uint64_t b_hi = umma::smem_desc_kmajor<kConvRowB>(b_addr + (kx * P) * C::kBBytes);
+              const uint64_t b_lo = umma::smem_desc_kmajor<kConvRowB>(b_addr + (kx * P + P - 1) * C::kBBytes);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t koff = (uint64_t)(k * 32 >> 4);  // 16 elements = 32 bytes along K
-            umma::mma_bf16_ss(tmem_main, adesc[0] + koff, bdesc[0] + koff, idesc,
-                              (it != it_begin || k != 0) ? 1u : 0u);
-            if (P == 2) {   // hi*lo + lo*hi (lo*lo ~ 2^-22 relative is dropped)
-              umma::mma_bf16_ss(tmem_cross, adesc[0] + koff, bdesc[P - 1] + koff, idesc, (it | k) != 0 ? 1u : 0u);
-              umma::mma_bf16_ss(tmem_cross, adesc[P - 1] + koff, bdesc[0] + koff, idesc, 1u);
+              for (int k = 0; k < kConvBK / 16; ++k) {
+                const uint64_t koff = (uint64_t)(k * 32 >> 4);  // 16 elements = 32 bytes along K
+                mma(tmem_main, a_hi + koff, b_hi + koff, idesc, (it != it_begin || kx != 0 || k != 0) ? 1u : 0u);
+                if (P == 2) {   // hi*lo + lo*hi (lo*lo ~ 2^-22 relative is dropped)
+                  mma(tmem_cross, a_hi + koff, b_lo + koff, idesc, (it | kx | k) != 0 ? 1u : 0u);
+                  mma(tmem_cross, a_lo + koff, b_hi + koff, idesc, 1u);
+                }
+              }
             }
+            commit(&empty_bar[s]);   // frees the smem stage (in both CTAs) once these MMAs have read it
+            }
+            __syncwarp();
           }
-          umma::mma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
+          if (umma::elect_one()) commit(&acc_full_bar[buf]);  // this chunk's accumulator (and all earlier MMAs) done
+          __syncwarp();
         }
-        umma::mma_commit(&acc_full_bar[buf]);  // this chunk's accumulator (and all earlier MMAs) done
       }
     }
   } else {
@@ -210,101 +426,76 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = (warp - 2) >> 2;                 // which half of the BN columns
     const int row = q * 32 + lane;                    // tile row = output pixel within the tile
     const uint32_t lane_col = ((uint32_t)(q * 32) << 16) + (uint32_t)(half * kHalf);
-    float acc[kHalf];
+    uint32_t gch = 0;
+    // CG == 2: "accumulator drained" is reported to the leader CTA, whose MMA warp owns the schedule
+    const uint32_t ae0 = CG == 2 ? umma::mapa_u32(umma::smem_u32(&acc_empty_bar[0]), 0) : 0u;
+    const uint32_t ae1 = CG == 2 ? umma::mapa_u32(umma::smem_u32(&acc_empty_bar[1]), 0) : 0u;
+    const uint32_t ce = CG == 2 ? umma::mapa_u32(umma::smem_u32(cross_empty_bar), 0) : 0u;
+    for (int tile = worker; tile < total_work; tile += n_workers) {
+      int g, x0, y0, n0;
+      decode(tile, g, x0, y0, n0);
+      float acc[kHalf];
 #pragma unroll
-    for (int j = 0; j < kHalf; ++j) acc[j] = 0.f;
-    for (int chunk = 0; chunk < n_chunks; ++chunk) {
-      const int buf = chunk & 1;
-      umma::mbar_wait(&acc_full_bar[buf], (chunk >> 1) & 1);
-      umma::tc_fence_after();
+      for (int j = 0; j < kHalf; ++j) acc[j] = 0.f;
+      for (int chunk = 0; chunk < n_chunks; ++chunk, ++gch) {
+        const int buf = gch & 1;
+        umma::mbar_wait(&acc_full_bar[buf], (gch >> 1) & 1);
+        umma::tc_fence_after();
 #pragma unroll
-      for (int gi = 0; gi < kGroups; ++gi) {
-        uint32_t r[16];
-        umma::tmem_ld_32x16(tmem_base + lane_col + (uint32_t)(buf * BN + gi * 16), r);
-        umma::tmem_ld_wait();
+        for (int gi = 0; gi < kGroups; ++gi) {
+          uint32_t r[16];
+          umma::tmem_ld_32x16(tmem_base + lane_col + (uint32_t)(buf * BN + gi * 16), r);
+          umma::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[gi * 16 + j] += __uint_as_float(r[j]);
-      }
-      if (P == 2) {
+          for (int j = 0; j < 16; ++j) acc[gi * 16 + j] += __uint_as_float(r[j]);
+        }
+        if (P == 2 && chunk == n_chunks - 1) {   // the last commit also covers every cross-term MMA
+#pragma unroll
+          for (int gi = 0; gi < kGroups; ++gi) {
+            uint32_t r[16];
+            umma::tmem_ld_32x16(tmem_base + lane_col + (uint32_t)(2 * BN + gi * 16), r);
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[gi * 16 + j] += __uint_as_float(r[j]);
+          }
+        }
         umma::tc_fence_before();
         __syncwarp();
-        if (lane == 0) umma::mbar_arrive(&acc_empty_bar[buf]);
-      }
-    }
-    if (P == 2) {   // the last acc_full commit also covers every cross-term MMA
-#pragma unroll
-      for (int gi = 0; gi < kGroups; ++gi) {
-        uint32_t r[16];
-        umma::tmem_ld_32x16(tmem_base + lane_col + (uint32_t)(2 * BN + gi * 16), r);
-        umma::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[gi * 16 + j] += __uint_as_float(r[j]);
-      }
-    }
-    const int py = y0 + row / p.TW, px = x0 + row % p.TW;
-    const long long pix = (long long)py * p.W_out + px + (long long)g * p.out_group_pix_stride;
-    const long long ch0 = (long long)p.cout_off + (long long)g * p.cout_group_stride + n0 + half * kHalf;
-#pragma unroll
-    for (int gi = 0; gi < kGroups; ++gi) {
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = __fmaf_rn(acc[gi * 16 + j], p.acc_scale, bias_s[half * kHalf + gi * 16 + j]);
-        v[j] = p.act == 0 ? x
-               : p.act == 1 ? gelu_erf(x)
-               : p.act == 2 ? __fdiv_rn(1.0f, 1.0f + expf(-x))     // torch.sigmoid
-               : p.act == 3 ? tanhf(x)                              // torch.tanh
-                            : fmaxf(x, 0.f);                        // ReLU
-      }
-      if (p.mask_src) {   // ReLU backward: pass the gradient where the forward activation was > 0
-        const __nv_bfloat16* m = p.mask_src + pix * p.Cout_total + ch0 + gi * 16;
-        uint32_t mb[8];
-        *(uint4*)&mb[0] = *(const uint4*)m;
-        *(uint4*)&mb[4] = *(const uint4*)(m + 8);
-        if (p.mask_planes == 2) {
-          uint32_t m2[8];
-          *(uint4*)&m2[0] = *(const uint4*)(m + p.mask_plane_stride);
-          *(uint4*)&m2[4] = *(const uint4*)(m + p.mask_plane_stride + 8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) mb[j] |= m2[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if ((mb[j] & 0x00007fffu) == 0u) v[2 * j] = 0.f;
-          if ((mb[j] & 0x7fff0000u) == 0u) v[2 * j + 1] = 0.f;
+        if (lane == 0) {
+          if (CG == 2) {
+            umma::mbar_arrive_cluster(buf ? ae1 : ae0);
+            if (P == 2 && chunk == n_chunks - 1) umma::mbar_arrive_cluster(ce);
+          } else {
+            umma::mbar_arrive(&acc_empty_bar[buf]);
+            if (P == 2 && chunk == n_chunks - 1) umma::mbar_arrive(cross_empty_bar);
+          }
         }
       }
-      if (p.out_t) {      // transposed split-plane copy: element (channel, pixel); lanes = consecutive pixels
-        const bool split_t = p.out_planes == 2;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          umma::store_split(p.out_t + (ch0 + gi * 16 + j) * (long long)p.ld_t + pix, p.out_t_plane_stride,
-                            split_t ? 2 : 1, v[j]);
-      }
-      if (p.out_fp32) {
-        float4* dst = (float4*)((float*)p.out + pix * p.Cout_total + ch0 + gi * 16);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      } else {
-        __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * p.Cout_total + ch0 + gi * 16;
-        const bool split = p.out_planes == 2;
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) umma::pack_split2(v[2 * j], v[2 * j + 1], split, hi[j], lo[j]);
-        uint4* dst = (uint4*)o;
-        dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        if (split) {
-          uint4* dst2 = (uint4*)(o + p.out_plane_stride);
-          dst2[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          dst2[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-        }
+      // ---- bias / activation / store (overlaps the next tile's main loop).  The activation is dispatched
+      // ONCE per tile to a specialised instance: a per-element runtime select made the compiler evaluate
+      // erff, expf, tanhf ... for every output (measured: ~9000 instructions per warp per tile).
+      const int py = y0 + row / p.TW, px = x0 + row % p.TW;
+      const long long pix = (long long)py * p.W_out + px + (long long)g * p.out_group_pix_stride;
+      const long long ch0 = (long long)p.cout_off + (long long)g * p.cout_group_stride + n0 + half * kHalf;
+      const float* bias = p.bias ? p.bias + n0 + half * kHalf : nullptr;
+      switch (p.act) {
+        case 0: conv_epilogue<0, kHalf>(acc, p, pix, ch0, bias); break;
+        case 1: conv_epilogue<1, kHalf>(acc, p, pix, ch0, bias); break;
+        case 2: conv_epilogue<2, kHalf>(acc, p, pix, ch0, bias); break;
+        case 3: conv_epilogue<3, kHalf>(acc, p, pix, ch0, bias); break;
+        case 4: conv_epilogue<4, kHalf>(acc, p, pix, ch0, bias); break;
+        case 5: conv_epilogue<5, kHalf>(acc, p, pix, ch0, bias); break;
+        default: conv_epilogue<6, kHalf>(acc, p, pix, ch0, bias); break;
       }
     }
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem_base, kTmemCols);
+  if (CG == 2) umma::cluster_sync();   // the peer may still be reading this CTA's shared memory / signalling its barriers
+  if (warp == 1) {
+    if (CG == 2) umma::tmem_dealloc_2cta(tmem_base, C::kTmemCols);
+    else umma::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------ bilinear 2x upsample
@@ -386,17 +577,28 @@ static PFN_cuTensorMapEncodeTiled get_encode_fn() {
   return fn;
 }
 
-template <int BN, int BK, int P, int STAGES>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int n_ctas,
-                       cudaStream_t stream) {
-  using S = ConvSmem<BN, BK, P, STAGES>;
-  auto kern = k_conv_umma<BN, BK, P, STAGES>;
+static int g_persistent = 1;
+static int g_enable_2cta = 1;
+
+template <int BN, int P, int NX, int CG>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+  using C = ConvCfg<BN, P, NX, CG>;
+  auto kern = k_conv_umma<BN, P, NX, CG>;
   static bool configured = false;
   if (!configured) {
-    HIMO_CUDA_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    HIMO_CUDA_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
     configured = true;
   }
-  kern<<<n_ctas, kConvThreads, S::kTotal, stream>>>(tmA, tmB, p);
+  const int work = p.total_tiles / CG;
+  int grid = (work < kNumSMs / CG || !g_persistent) ? work : kNumSMs / CG;   // persistent: one CTA (pair) per SM (pair)
+  grid *= CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = C::kTotal; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  HIMO_CUDA_RET(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   HIMO_LAUNCH_RET();
   return HIMO_OK;
 }
@@ -405,18 +607,27 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
 
 using namespace himo;
 
-static int g_flush_iters = 8;
-// Tuning knob (process-wide): length of one TMEM accumulation chain in k-iterations of 32 channels.
-extern "C" int himo_conv_set_flush_iters(int iters) {
-  if (iters < 1) return HIMO_ERR_ARG;
-  g_flush_iters = iters;
+static int g_flush_mmas = 48;
+static int g_disable_halo = 0;
+// Debug / A-B knob: 1 disables the haloed-row reuse (every tap loads its own A tile).
+extern "C" int himo_conv_set_halo(int enable) { g_disable_halo = enable ? 0 : 1; return HIMO_OK; }
+// A/B knob: 0 disables the CTA-pair (cta_group::2) path.
+extern "C" int himo_conv_set_2cta(int enable) { g_enable_2cta = enable ? 1 : 0; return HIMO_OK; }
+// A/B knob: 0 launches one CTA per tile instead of the persistent one-CTA-per-SM tile loop.
+extern "C" int himo_conv_set_persistent(int enable) { g_persistent = enable ? 1 : 0; return HIMO_OK; }
+// Tuning knob (process-wide): number of hi*hi MMAs (K = 16 each) accumulated in tensor memory before the
+// partial sum is drained into fp32 registers (split mode).  Kept under the historical name.
+extern "C" int himo_conv_set_flush_iters(int mmas) {
+  if (mmas < 1) return HIMO_ERR_ARG;
+  g_flush_mmas = mmas;
   return HIMO_OK;
 }
 
 extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
-  if (!d || !d->in || !d->wgt || !d->out) return HIMO_ERR_ARG;
+  if (!d || !d->in || !d->wgt || (!d->out && d->act < 5)) return HIMO_ERR_ARG;
+  if (d->act >= 5 && (!d->aux_h || !d->aux_z || !d->out2 || d->aux_ld % 16)) return HIMO_ERR_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
-  constexpr int BK = 32;
+  constexpr int BK = kConvBK;
   const int P = d->in_planes;
   if (P != 1 && P != 2) return HIMO_ERR_ARG;
   if (d->ksize != 1 && d->ksize != 3) return HIMO_ERR_UNSUPPORTED;
@@ -440,6 +651,14 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
   else return HIMO_ERR_UNSUPPORTED;
   const int groups = d->n_groups > 0 ? d->n_groups : 1;
 
+  // CTA pairs (cta_group::2) whenever the M tiles pair up
+  const int m_tiles_total = (W_out / TW) * (H_out / TH);
+  // (measured: pairing pays once a tile carries >= ~48 hi*hi MMAs; below that the pair's lock-step costs more
+  // than the halved weight traffic saves)
+  const int main_mmas_per_tile = d->ksize * d->ksize * (d->Cin / BK) * 2;
+  const int CGsel = (g_enable_2cta && m_tiles_total % 2 == 0 && main_mmas_per_tile >= 48) ? 2 : 1;
+  // halo mode: 3x3, stride 1, full 128-pixel row tiles -> one haloed A load feeds the three kx taps
+  const bool halo = d->ksize == 3 && d->stride == 1 && TW == 128 && TH == 1 && !g_disable_halo;
   PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
   if (!enc) return HIMO_ERR_UNSUPPORTED;
   CUtensorMap tmA, tmB;
@@ -447,7 +666,7 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin_total, (cuuint64_t)d->W_in, (cuuint64_t)d->H_in, (cuuint64_t)P};
     cuuint64_t strides[3] = {(cuuint64_t)d->Cin_total * 2, (cuuint64_t)d->W_in * d->Cin_total * 2,
                              (cuuint64_t)d->in_plane_stride * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)((TW - 1) * d->stride + 1),
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(halo ? TW + 2 : (TW - 1) * d->stride + 1),
                          (cuuint32_t)((TH - 1) * d->stride + 1), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)d->in, dims, strides, box, estr,
@@ -460,7 +679,7 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
   {
     cuuint64_t dims[3] = {(cuuint64_t)k_total, (cuuint64_t)d->Cout, (cuuint64_t)P};
     cuuint64_t strides[2] = {(cuuint64_t)k_total * 2, (cuuint64_t)d->Cout * k_total * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(BN / CGsel), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d->wgt, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
@@ -476,21 +695,30 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
   p.W_out = W_out; p.Cout_total = d->Cout_total; p.cout_off = d->cout_off;
   p.cout_group_stride = d->cout_group_stride; p.act = d->act; p.out_fp32 = d->out_fp32;
   p.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
-  p.flush_iters = g_flush_iters;   // k-iterations (2 hi*hi MMAs each) per TMEM accumulation chain
+  {  // stages per accumulation chain: a stage issues 2*NX hi*hi MMAs
+    const int per_stage = 2 * (halo ? 3 : 1);
+    p.flush_stages = g_flush_mmas / per_stage > 0 ? g_flush_mmas / per_stage : 1;
+  }
   p.out_t = (__nv_bfloat16*)d->out_t; p.out_t_plane_stride = d->out_t_plane_stride; p.ld_t = d->ld_t;
   p.mask_src = (const __nv_bfloat16*)d->mask_src; p.mask_plane_stride = d->mask_plane_stride;
   p.mask_planes = d->mask_planes;
   p.b_group_k_stride = d->b_group_k_stride; p.out_group_pix_stride = d->out_group_pix_stride;
   p.stop_flag = d->stop_flag;
-  const int n_ctas = p.tiles_x * p.tiles_y * p.n_tiles_n * groups;
-#define HIMO_CONV_CASE(bn, pp, st) \
-  if (BN == bn && P == pp) return launch_conv<bn, BK, pp, st>(tmA, tmB, p, n_ctas, stream);
-  HIMO_CONV_CASE(128, 2, 6)
-  HIMO_CONV_CASE(96, 2, 7)
-  HIMO_CONV_CASE(64, 2, 4)
-  HIMO_CONV_CASE(128, 1, 6)
-  HIMO_CONV_CASE(96, 1, 6)
-  HIMO_CONV_CASE(64, 1, 8)
+  p.aux_h = d->aux_h; p.aux_z = d->aux_z; p.aux_ld = d->aux_ld;
+  p.out2 = (__nv_bfloat16*)d->out2; p.out2_plane_stride = d->out2_plane_stride; p.out2_ld = d->out2_ld;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles_n * groups;
+#define HIMO_CONV_CASE(bn, pp)                                                                        \
+  if (BN == bn && P == pp) {                                                                          \
+    if (CGsel == 2)                                                                                   \
+      return halo ? launch_conv<bn, pp, 3, 2>(tmA, tmB, p, stream) : launch_conv<bn, pp, 1, 2>(tmA, tmB, p, stream); \
+    return halo ? launch_conv<bn, pp, 3, 1>(tmA, tmB, p, stream) : launch_conv<bn, pp, 1, 1>(tmA, tmB, p, stream);   \
+  }
+  HIMO_CONV_CASE(128, 2)
+  HIMO_CONV_CASE(96, 2)
+  HIMO_CONV_CASE(64, 2)
+  HIMO_CONV_CASE(128, 1)
+  HIMO_CONV_CASE(96, 1)
+  HIMO_CONV_CASE(64, 1)
 #undef HIMO_CONV_CASE
   return HIMO_ERR_UNSUPPORTED;
 }

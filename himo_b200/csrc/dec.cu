@@ -17,7 +17,17 @@ namespace himo {
 
 using umma::store_split;
 
-// one warp per point; lanes sweep the 288 channels of [before(96) | after(96) | offset feature(96)]
+// 8 consecutive channels per thread: 2 x float4 in, one 16-byte store per plane out
+__device__ __forceinline__ void store_split8(__nv_bfloat16* dst, long long plane_stride, int planes, const float* v) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma::pack_split2(v[2 * k], v[2 * k + 1], planes == 2, hi[k], lo[k]);
+  *(uint4*)dst = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (planes == 2) *(uint4*)(dst + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// one warp per point; each lane owns 8-channel chunks of the 288 = [before(96) | after(96) | offset feature(96)]
+// channels, so every global access is a 16/32-byte vector.
 __global__ void __launch_bounds__(256)
 k_dec_gather(DecGatherArgs a) {
   const int lane = threadIdx.x & 31;
@@ -29,45 +39,45 @@ k_dec_gather(DecGatherArgs a) {
     float* h = a.h32 + (size_t)i * 192;
     __nv_bfloat16* hx = a.hx_planes + (size_t)i * 288;
     __nv_bfloat16* rhx = a.rhx_planes + (size_t)i * 288;
-    if (key < 0) {
-      for (int c = lane; c < 192; c += 32) h[c] = 0.f;
-      for (int c = lane; c < 288; c += 32) {
-        store_split(hx + c, a.plane_stride, a.planes, 0.f);
-        if (c >= 192) store_split(rhx + c, a.plane_stride, a.planes, 0.f);
-      }
-      continue;
-    }
-    // before_pseudoimage[:, y, x]: the (exact fp32) voxel feature of each frame, zero where empty
-    for (int f = 0; f < a.n_frames; ++f) {
-      const unsigned* bm = a.bitmap + (size_t)f * a.n_words;
-      float v = 0.f;
-      if ((__ldg(bm + (key >> 5)) >> (key & 31)) & 1u) {
-        const int r = bitmap_rank_lb(bm, a.word_prefix + (size_t)f * a.n_words, key);
-        v = __ldg(a.voxel_feats + ((size_t)f * a.n_max + r) * 32 + lane);
-      }
-      h[f * 32 + lane] = v;
-      store_split(hx + f * 32 + lane, a.plane_stride, a.planes, v);
-    }
-    // after_pseudoimage[:, y, x]
-    const float* av = a.after + (size_t)key * a.c_after;
-    for (int c = lane; c < 96; c += 32) {
-      const float v = __ldg(av + c);
-      h[96 + c] = v;
-      store_split(hx + 96 + c, a.plane_stride, a.planes, v);
-    }
     // point_offsets = p - ((c * voxel_size + min) + voxel_size/2), every step rounded to fp32
     // (DynamicVoxelizer._get_point_offsets, encoder.py:506-523)
-    const int cy = key / a.gx, cx = key - cy * a.gx;
-    const float ox = p.x - __fadd_rn(__fadd_rn(__fmul_rn((float)cx, a.vx), a.x_min), a.hx);
-    const float oy = p.y - __fadd_rn(__fadd_rn(__fmul_rn((float)cy, a.vy), a.y_min), a.hy);
-    const float oz = p.z - __fadd_rn(__fadd_rn(__fmul_rn(0.f, a.vz), a.z_min), a.hz);
-    for (int c = lane; c < 96; c += 32) {
-      float v = __ldg(a.w_off + c * 3) * ox;
-      v = fmaf(__ldg(a.w_off + c * 3 + 1), oy, v);
-      v = fmaf(__ldg(a.w_off + c * 3 + 2), oz, v);
-      v += __ldg(a.b_off + c);
-      store_split(hx + 192 + c, a.plane_stride, a.planes, v);
-      store_split(rhx + 192 + c, a.plane_stride, a.planes, v);
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (key >= 0) {
+      const int cy = key / a.gx, cx = key - cy * a.gx;
+      ox = p.x - __fadd_rn(__fadd_rn(__fmul_rn((float)cx, a.vx), a.x_min), a.hx);
+      oy = p.y - __fadd_rn(__fadd_rn(__fmul_rn((float)cy, a.vy), a.y_min), a.hy);
+      oz = p.z - __fadd_rn(__fadd_rn(__fmul_rn(0.f, a.vz), a.z_min), a.hz);
+    }
+    for (int ch = lane; ch < 36; ch += 32) {
+      const int c0 = ch * 8;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (key >= 0) {
+        if (ch < 12) {
+          // before_pseudoimage[:, y, x]: the exact fp32 voxel feature of frame f, zero where that frame is empty
+          const int f = ch >> 2;
+          const unsigned* bm = a.bitmap + (size_t)f * a.n_words;
+          if ((__ldg(bm + (key >> 5)) >> (key & 31)) & 1u) {
+            const int r = bitmap_rank_lb(bm, a.word_prefix + (size_t)f * a.n_words, key);
+            const float4* src = (const float4*)(a.voxel_feats + ((size_t)f * a.n_max + r) * 32 + (ch & 3) * 8);
+            *(float4*)&v[0] = __ldg(src); *(float4*)&v[4] = __ldg(src + 1);
+          }
+        } else if (ch < 24) {
+          const float4* src = (const float4*)(a.after + (size_t)key * a.c_after + (c0 - 96));   // after[:, y, x]
+          *(float4*)&v[0] = __ldg(src); *(float4*)&v[4] = __ldg(src + 1);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = c0 - 192 + k;
+            float t = __ldg(a.w_off + c * 3) * ox;
+            t = fmaf(__ldg(a.w_off + c * 3 + 1), oy, t);
+            t = fmaf(__ldg(a.w_off + c * 3 + 2), oz, t);
+            v[k] = t + __ldg(a.b_off + c);
+          }
+        }
+      }
+      if (ch < 24) { *(float4*)(h + c0) = *(float4*)&v[0]; *(float4*)(h + c0 + 4) = *(float4*)&v[4]; }
+      store_split8(hx + c0, a.plane_stride, a.planes, v);
+      if (ch >= 24) store_split8(rhx + c0, a.plane_stride, a.planes, v);
     }
   }
 }
@@ -76,13 +86,15 @@ k_dec_gather(DecGatherArgs a) {
 __global__ void __launch_bounds__(256)
 k_dec_rh(const float* __restrict__ zr, const float* __restrict__ h32, int n_pad,
          __nv_bfloat16* __restrict__ rhx, int planes, long long plane_stride) {
-  const long long total = (long long)n_pad * 192;
+  const long long total = (long long)n_pad * 24;          // 192 / 8 chunks per point
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
-    const long long i = t / 192;
-    const int c = (int)(t - i * 192);
-    const float r = zr[i * 384 + 192 + c];
-    store_split(rhx + i * 288 + c, plane_stride, planes, r * h32[t]);
+    const long long i = t / 24;
+    const int c = (int)(t - i * 24) * 8;
+    const float4 r0 = *(const float4*)(zr + i * 384 + 192 + c), r1 = *(const float4*)(zr + i * 384 + 196 + c);
+    const float4 h0 = *(const float4*)(h32 + i * 192 + c), h1 = *(const float4*)(h32 + i * 192 + c + 4);
+    const float v[8] = {r0.x * h0.x, r0.y * h0.y, r0.z * h0.z, r0.w * h0.w, r1.x * h1.x, r1.y * h1.y, r1.z * h1.z, r1.w * h1.w};
+    store_split8(rhx + i * 288 + c, plane_stride, planes, v);
   }
 }
 
@@ -90,15 +102,20 @@ k_dec_rh(const float* __restrict__ zr, const float* __restrict__ h32, int n_pad,
 __global__ void __launch_bounds__(256)
 k_dec_update(const float* __restrict__ zr, const float* __restrict__ q, float* __restrict__ h32, int n_pad,
              __nv_bfloat16* __restrict__ hx, int planes, long long plane_stride) {
-  const long long total = (long long)n_pad * 192;
+  const long long total = (long long)n_pad * 24;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
-    const long long i = t / 192;
-    const int c = (int)(t - i * 192);
-    const float z = zr[i * 384 + c];
-    const float hn = __fadd_rn(__fmul_rn(1.0f - z, h32[t]), __fmul_rn(z, q[t]));
-    h32[t] = hn;
-    store_split(hx + i * 288 + c, plane_stride, planes, hn);
+    const long long i = t / 24;
+    const int c = (int)(t - i * 24) * 8;
+    float z[8], qq[8], h[8], hn[8];
+    *(float4*)&z[0] = *(const float4*)(zr + i * 384 + c); *(float4*)&z[4] = *(const float4*)(zr + i * 384 + c + 4);
+    *(float4*)&qq[0] = *(const float4*)(q + i * 192 + c); *(float4*)&qq[4] = *(const float4*)(q + i * 192 + c + 4);
+    *(float4*)&h[0] = *(const float4*)(h32 + i * 192 + c); *(float4*)&h[4] = *(const float4*)(h32 + i * 192 + c + 4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hn[k] = __fadd_rn(__fmul_rn(1.0f - z[k], h[k]), __fmul_rn(z[k], qq[k]));
+    *(float4*)(h32 + i * 192 + c) = *(float4*)&hn[0];
+    *(float4*)(h32 + i * 192 + c + 4) = *(float4*)&hn[4];
+    store_split8(hx + i * 288 + c, plane_stride, planes, hn);
   }
 }
 

@@ -72,6 +72,18 @@ static int conv(const Act& in, int cin_off, int cin, int groups, const void* w, 
   return himo_conv2d_nhwc(&d, stream);
 }
 
+// ConvGRU GEMM with the gate math fused into the epilogue (conv.cu act 5 / 6); z lives in zbuf [n][192].
+static int gru_gemm(const Act& in, const void* w, const float* bias, int cout, int act, float acc_scale, float* h32,
+                    float* zbuf, __nv_bfloat16* out2, long long ps, int planes, cudaStream_t stream) {
+  himo_conv_desc d = {};
+  d.in = in.p; d.in_planes = planes; d.in_plane_stride = in.plane_stride();
+  d.H_in = in.H; d.W_in = in.W; d.Cin_total = in.C; d.Cin = in.C;
+  d.wgt = w; d.bias = bias; d.Cout = cout; d.ksize = 1; d.stride = 1;
+  d.out = nullptr; d.out_planes = planes; d.Cout_total = cout; d.act = act; d.acc_scale = acc_scale; d.n_groups = 1;
+  d.aux_h = h32; d.aux_z = zbuf; d.aux_ld = 192; d.out2 = out2; d.out2_plane_stride = ps; d.out2_ld = 288;
+  return himo_conv2d_nhwc(&d, stream);
+}
+
 #define HIMO_RET(expr) do { int _s = (expr); if (_s != HIMO_OK) return _s; } while (0)
 
 }  // namespace himo
@@ -169,6 +181,9 @@ extern "C" int himo_deflowpp_forward(const himo_deflowpp_weights* w, const himo_
     HIMO_RET(dec_gather(g, stream));
     Act HX{nb.hx, n_pad / 128, 128, 288}, RHX{nb.rhx, n_pad / 128, 128, 288}, none{nullptr, 0, 0, 0};
     for (int it = 0; it < io->num_iters; ++it) {
+      // The gate math could ride in the GEMM epilogue (conv.cu act 5/6, kept for reference) but measured
+      // 2x slower: the per-row global reads of h and z sit on the tile's critical path.  Separate,
+      // fully vectorised element-wise kernels are cheaper.
       HIMO_RET(conv(HX, 0, 288, 1, w->gru_zr_w, w->gru_zr_b, 384, 1, 1, 2, none, 0, P, stream, w->gru_zr_s, nb.zr));
       HIMO_RET(dec_rh(nb.zr, nb.h32, n_pad, nb.rhx, P, ps, stream));
       HIMO_RET(conv(RHX, 0, 288, 1, w->gru_q_w, w->gru_q_b, 192, 1, 1, 3, none, 0, P, stream, w->gru_q_s, nb.q));

@@ -107,7 +107,7 @@ int himo_chamfer_backward(const float* pc0, int n0, const float* pc1, int n1, co
  *   bias    [Cout] f32 or NULL (BatchNorm folded in by the host)
  *   out     NHWC, channels [cout_off + g*cout_group_stride, +Cout) of Cout_total; bf16 planes
  *           (out_planes 1|2) or fp32 (out_fp32 = 1)
- *   ksize 1|3 (padding ksize/2), stride 1|2, act 0 none | 1 exact-erf GELU | 2 sigmoid | 3 tanh | 4 ReLU
+ *   ksize 1|3 (padding ksize/2), stride 1|2, act 0 none | 1 exact-erf GELU | 2 sigmoid | 3 tanh | 4 ReLU | 5,6 fused ConvGRU
  */
 typedef struct himo_conv_desc {
   const void* in;
@@ -135,11 +135,21 @@ typedef struct himo_conv_desc {
   long long out_group_pix_stride; /* split-K: output row offset per group */
   long long b_k_total;        /* row length of the weight operand when it is not ksize^2*Cin */
   const int32_t* stop_flag;   /* device flag; non-zero makes the launch a no-op (early stopping) */
+  /* fused ConvGRU epilogues (OSF/src/models/basic/decoder.py:185-192): act 5 = [z|r] GEMM -> z to aux_z,
+   * split(r*h) to out2; act 6 = q GEMM -> h = (1-z)h + z*tanh(.) to aux_h and split(h) to out2 */
+  float* aux_h; float* aux_z; int aux_ld;
+  void* out2; long long out2_plane_stride; int out2_ld;
 } himo_conv_desc;
 int himo_conv2d_nhwc(const himo_conv_desc* desc, void* stream);
-/* Split-mode accuracy/speed knob: k-iterations (32 input channels each) accumulated in tensor memory
- * before the partial sum is drained into fp32 registers (default 8).  Process-wide. */
-int himo_conv_set_flush_iters(int iters);
+/* Split-mode accuracy/speed knob: hi*hi MMAs (K = 16 each) accumulated in tensor memory before the partial
+ * sum is drained into fp32 registers (default 48).  Process-wide. */
+int himo_conv_set_flush_iters(int mmas);
+/* A/B knob: 0 disables the haloed-row reuse of the activation tile across the kx taps (default on). */
+int himo_conv_set_halo(int enable);
+/* A/B knob: 0 launches one CTA per output tile instead of the persistent tile loop (default on). */
+int himo_conv_set_persistent(int enable);
+/* A/B knob: 0 disables the CTA-pair path (tcgen05.mma.cta_group::2 over a cluster of 2; default on). */
+int himo_conv_set_2cta(int enable);
 /* replaces: F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) of
  *           BilinearDecoder.forward (OSF/src/models/basic/unet.py:7-16); in [h][w][c] planes ->
  *           channels [cout_off, +c) of out [2h][2w][Cout_total] planes. */

@@ -5,7 +5,7 @@ from himo_b200 import deflowpp, frames, weights
 from oracle import deflowpp_ref
 
 kind, n, seed = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-if len(sys.argv) > 4:
+if len(sys.argv) > 4 and sys.argv[4] != '-':
     from himo_b200 import _lib
     _lib.lib().himo_conv_set_flush_iters(int(sys.argv[4]))
     print("flush_iters", sys.argv[4])
