@@ -100,6 +100,91 @@ class SeFlowPPEngine:
         self.stream.synchronize()
         return host.numpy().copy()
 
+    # ------------------------------------------------------------------ pipelined streaming API
+    def infer_stream(self, frames):
+        """Iterate over host frames and yield `final_flow` arrays in order, with the H2D copy of frame i+1
+        and the D2H copy of frame i-1 overlapping the network of frame i (three CUDA streams, two slots).
+        Same results as `infer`; this is the call the multi-frame drivers (runner.run_save, bench.py) use."""
+        dev = self.device
+        if not hasattr(self, "_s_in"):
+            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._slots = [dict(pin={k: _Pinned(torch.float32) for k in ("pch1", "pc0", "pc1", "pc0_all", "out")},
+                                pin_idx=_Pinned(torch.int32)) for _ in range(2)]
+        pending = []          # (slot, ev_out, n_all)
+        ev_done = [None, None]
+
+        def launch(i, frame):
+            slot = self._slots[i % 2]
+            pc0_all = np.asarray(frame["pc0"], dtype=np.float32)[:, :3]
+            pc0, keep0 = self._strip(frame["pc0"], frame.get("gm0"))
+            pc1, _ = self._strip(frame["pc1"], frame.get("gm1"))
+            pch1, _ = self._strip(frame["pch1"], frame.get("gmh1"))
+            T0 = cal_pose0to1(torch.as_tensor(frame["pose0"]), torch.as_tensor(frame["pose1"]))
+            Th = cal_pose0to1(torch.as_tensor(frame["poseh1"]), torch.as_tensor(frame["pose1"]))
+            n_all = pc0_all.shape[0]
+            h2d = d2h = 0
+            with torch.cuda.stream(self._s_in):
+                if ev_done[i % 2] is not None:          # the network has finished reading this slot's inputs
+                    self._s_in.wait_event(ev_done[i % 2])
+                devs = {}
+                for key, arr in (("pc0", pc0), ("pc1", pc1), ("pch1", pch1)):
+                    pin = slot["pin"][key].get(arr.shape[0])
+                    pin.numpy()[...] = arr
+                    d = torch.empty((arr.shape[0], 3), dtype=torch.float32, device=dev)
+                    d.copy_(pin, non_blocking=True)
+                    devs[key] = d
+                    h2d += arr.shape[0] * 12
+                if keep0 is not None:
+                    pin = slot["pin"]["pc0_all"].get(n_all)
+                    pin.numpy()[...] = pc0_all
+                    d0_all = torch.empty((n_all, 3), dtype=torch.float32, device=dev)
+                    d0_all.copy_(pin, non_blocking=True)
+                    src = np.full(n_all, -1, np.int32)
+                    src[keep0] = np.arange(int(keep0.sum()), dtype=np.int32)
+                    pidx = slot["pin_idx"].get(n_all, 1)
+                    pidx.numpy()[...] = src
+                    src_dev = torch.empty(n_all, dtype=torch.int32, device=dev)
+                    src_dev.copy_(pidx, non_blocking=True)
+                    h2d += n_all * 16
+                else:
+                    d0_all, src_dev = devs["pc0"], None
+                T12 = T0[:3, :4].contiguous().float().flatten().pin_memory().to(dev, non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self._s_in)
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ev_in)
+                out = self.net.forward_triple(devs["pch1"], devs["pc0"], devs["pc1"], Th, T0, compact=False)
+                final = torch.empty((n_all, 3), dtype=torch.float32, device=dev)
+                st = _lib.lib().himo_final_flow(_lib.ptr(d0_all), n_all, _lib.ptr(T12), _lib.ptr(out["flow_all"]),
+                                                _lib.ptr(src_dev), _lib.ptr(final), _lib.stream_ptr(dev))
+                _lib.check(st, "himo_final_flow")
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                ev_done[i % 2] = ev
+                for t in list(devs.values()) + [d0_all, T12, final] + ([src_dev] if src_dev is not None else []):
+                    t.record_stream(self.stream)
+            with torch.cuda.stream(self._s_out):
+                self._s_out.wait_event(ev)
+                host = slot["pin"]["out"].get(n_all)
+                host.copy_(final, non_blocking=True)
+                final.record_stream(self._s_out)
+                ev_out = torch.cuda.Event()
+                ev_out.record(self._s_out)
+            self.h2d_bytes, self.d2h_bytes = h2d, n_all * 12
+            return (host, ev_out)
+
+        def collect(item):
+            host, ev_out = item
+            ev_out.synchronize()
+            return host.numpy().copy()
+
+        for i, frame in enumerate(frames):
+            pending.append(launch(i, frame))
+            if len(pending) == 2:            # the slot about to be reused must be drained first
+                yield collect(pending.pop(0))
+        while pending:
+            yield collect(pending.pop(0))
+
 
 class FastNSFEngine:
     """`InferenceRunner._process_step` for FastNSF (OSF/src/runner.py:130-155): ground removal, per-pair
