@@ -43,6 +43,8 @@ def lib() -> ctypes.CDLL:
     _sig(L, "himo_chamfer_workspace_bytes", c_size_t, [c_int, c_int])
     _sig(L, "himo_chamfer_forward", c_int,
          [P, c_int, P, c_int, P, P, P, P, c_float, P, c_size_t, P])
+    _sig(L, "himo_chamfer_forward_radius", c_int,
+         [P, c_int, P, c_int, P, P, P, P, c_float, P, c_size_t, P])
     _sig(L, "himo_chamfer_backward", c_int, [P, c_int, P, c_int, P, P, P, P, P, P, P])
     for name, restype, argtypes in _LATE_SIGS:
         if hasattr(L, name):

@@ -44,6 +44,7 @@ struct ConvParams {
   int out_planes;
   long long out_plane_stride;
   int W_out, Cout_total, cout_off, cout_group_stride;
+  int Cout;                         // output channels of one group (bias length)
   int act, out_fp32;
   float acc_scale;
   int flush_stages;
@@ -96,10 +97,12 @@ struct ConvCfg {
   static constexpr int kBBytes = kBRows * kConvRowB;
   static constexpr int kStageBytes = P * kABytes + NX * P * kBBytes;
   static constexpr int kTxBytes = P * kARowsTx * kConvRowB + NX * P * kBBytes;
-  static constexpr int kStagesRaw = (224 * 1024 - 1024) / kStageBytes;
+  static constexpr int kStagesRaw = (220 * 1024) / kStageBytes;
   static constexpr int STAGES = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 512 + 128;              // barriers + alignment slack
+  static constexpr int kBiasOffset = kBarOffset + 512;               // fp32 bias vector staged once per CTA
+  static constexpr int kMaxBias = 1024;
+  static constexpr int kTotal = kBiasOffset + kMaxBias * 4 + 128;   // barriers + bias + alignment slack
   static constexpr int kUsedCols = P == 2 ? 3 * BN : 2 * BN;
   static constexpr int kTmemCols = kUsedCols <= 64 ? 64 : kUsedCols <= 128 ? 128 : kUsedCols <= 256 ? 256 : 512;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
@@ -234,6 +237,71 @@ for (int gi = 0; gi < kHalfT / 16; ++gi) {
 }
 }
 
+// Common-path tile epilogue for 16 accumulator columns of one output pixel: scale + bias, activation, then
+// either 16 fp32 values or the split 16-bit planes.  Deliberately NOT inlined: the fully unrolled epilogue of
+// a 128-column tile was ~50 KB of straight-line code per activation, executed once per tile, and the
+// profile (profiles/r01_enc2_source_stalls.txt) showed the epilogue warps starving on instruction fetch
+// (stall_no_inst).  One ~700-instruction body per activation stays resident in the instruction caches.
+struct EpiOut {
+  void* out;                 // address of this pixel's first channel of the group (plane 0)
+  long long plane_stride_b;  // bytes between the hi and lo planes (split output)
+  float scale;
+  int mode;                  // 0 = fp32, 1 = one bf16 plane, 2 = split fp16 planes
+};
+template <int ACT>
+__device__ __noinline__ void epi_store16(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7,
+                                         float a8, float a9, float a10, float a11, float a12, float a13, float a14,
+                                         float a15, const float* __restrict__ bias_s, EpiOut o) {
+  float v[16] = {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15};
+  float b[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *(float4*)&b[4 * j] = *(const float4*)(bias_s + 4 * j);   // shared-memory broadcast
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float x = __fmaf_rn(v[j], o.scale, b[j]);
+    if (ACT == 1) v[j] = gelu_erf(x);
+    else if (ACT == 2) v[j] = fast_sigmoid(x);
+    else if (ACT == 3) v[j] = fast_tanh(x);
+    else if (ACT == 4) v[j] = fmaxf(x, 0.f);
+    else v[j] = x;
+  }
+  if (o.mode == 0) {
+    float4* dst = (float4*)o.out;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+    const bool split = o.mode == 2;
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) umma::pack_split2(v[2 * j], v[2 * j + 1], split, hi[j], lo[j]);
+    uint4* dst = (uint4*)o.out;
+    dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    if (split) {
+      uint4* dst2 = (uint4*)((char*)o.out + o.plane_stride_b);
+      dst2[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      dst2[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    }
+  }
+}
+
+template <int ACT, int kHalfT>
+__device__ __forceinline__ void conv_epilogue_fast(const float* acc, const ConvParams& p, long long pix, long long ch0,
+                                                   const float* bias_s) {
+  EpiOut o;
+  o.scale = p.acc_scale;
+  o.mode = p.out_fp32 ? 0 : (p.out_planes == 2 ? 2 : 1);
+  o.plane_stride_b = p.out_plane_stride * 2;
+  const long long elem = pix * p.Cout_total + ch0;
+#pragma unroll
+  for (int gi = 0; gi < kHalfT / 16; ++gi) {
+    o.out = p.out_fp32 ? (void*)((float*)p.out + elem + gi * 16) : (void*)((__nv_bfloat16*)p.out + elem + gi * 16);
+    const float* a = acc + gi * 16;
+    epi_store16<ACT>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14],
+                     a[15], bias_s + gi * 16, o);
+  }
+}
+
 // Accumulation scheme.  tcgen05 adds every MMA into the fp32 TMEM accumulator with truncation, so a long
 // accumulation chain drifts by ~0.5 ulp per MMA (measured: error grows linearly with K).  To stay fp32-class
 //   * split mode: the small cross products hi*lo + lo*hi go to their own accumulator ("cross") and never
@@ -262,6 +330,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* acc_empty_bar = acc_full_bar + 2;      // [2]
   uint64_t* cross_empty_bar = acc_empty_bar + 2;   // [1]
   uint32_t* tmem_ptr_smem = (uint32_t*)(cross_empty_bar + 1);
+  float* bias_smem = (float*)(smem + C::kBiasOffset);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.stop_flag && *p.stop_flag) return;   // uniform across the grid
@@ -291,6 +360,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (CG == 2) umma::tmem_alloc_2cta(tmem_ptr_smem, C::kTmemCols);
     else umma::tmem_alloc(tmem_ptr_smem, C::kTmemCols);
   }
+  for (int i = threadIdx.x; i < p.Cout && i < C::kMaxBias; i += kConvThreads) bias_smem[i] = p.bias ? __ldg(p.bias + i) : 0.f;
   umma::tc_fence_before();
   __syncthreads();
   if (CG == 2) umma::cluster_sync();       // peer barriers are initialised before anything signals them
@@ -448,24 +518,23 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int buf = gch & 1;
         umma::mbar_wait(&acc_full_bar[buf], (gch >> 1) & 1);
         umma::tc_fence_after();
+        auto drain = [&](uint32_t col0) {   // acc += TMEM[col0 .. col0 + kHalf): two 16-column loads in flight per wait
 #pragma unroll
-        for (int gi = 0; gi < kGroups; ++gi) {
-          uint32_t r[16];
-          umma::tmem_ld_32x16(tmem_base + lane_col + (uint32_t)(buf * BN + gi * 16), r);
-          umma::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[gi * 16 + j] += __uint_as_float(r[j]);
-        }
-        if (P == 2 && chunk == n_chunks - 1) {   // the last commit also covers every cross-term MMA
-#pragma unroll
-          for (int gi = 0; gi < kGroups; ++gi) {
-            uint32_t r[16];
-            umma::tmem_ld_32x16(tmem_base + lane_col + (uint32_t)(2 * BN + gi * 16), r);
+          for (int gi = 0; gi < kGroups; gi += 2) {
+            uint32_t r0[16], r1[16];
+            umma::tmem_ld_32x16(tmem_base + lane_col + col0 + (uint32_t)(gi * 16), r0);
+            if (gi + 1 < kGroups) umma::tmem_ld_32x16(tmem_base + lane_col + col0 + (uint32_t)(gi * 16 + 16), r1);
             umma::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[gi * 16 + j] += __uint_as_float(r[j]);
+            for (int j = 0; j < 16; ++j) acc[gi * 16 + j] += __uint_as_float(r0[j]);
+            if (gi + 1 < kGroups) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[gi * 16 + 16 + j] += __uint_as_float(r1[j]);
+            }
           }
-        }
+        };
+        drain((uint32_t)(buf * BN));
+        if (P == 2 && chunk == n_chunks - 1) drain((uint32_t)(2 * BN));   // the last commit also covers every cross-term MMA
         umma::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -485,6 +554,17 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const long long pix = (long long)py * p.W_out + px + (long long)g * p.out_group_pix_stride;
       const long long ch0 = (long long)p.cout_off + (long long)g * p.cout_group_stride + n0 + half * kHalf;
       const float* bias = p.bias ? p.bias + n0 + half * kHalf : nullptr;
+      if (p.act < 5 && !p.out_t && !p.mask_src && p.Cout <= C::kMaxBias) {
+        const float* bias_s = bias_smem + n0 + half * kHalf;
+        switch (p.act) {
+          case 0: conv_epilogue_fast<0, kHalf>(acc, p, pix, ch0, bias_s); break;
+          case 1: conv_epilogue_fast<1, kHalf>(acc, p, pix, ch0, bias_s); break;
+          case 2: conv_epilogue_fast<2, kHalf>(acc, p, pix, ch0, bias_s); break;
+          case 3: conv_epilogue_fast<3, kHalf>(acc, p, pix, ch0, bias_s); break;
+          default: conv_epilogue_fast<4, kHalf>(acc, p, pix, ch0, bias_s); break;
+        }
+        continue;
+      }
       switch (p.act) {
         case 0: conv_epilogue<0, kHalf>(acc, p, pix, ch0, bias); break;
         case 1: conv_epilogue<1, kHalf>(acc, p, pix, ch0, bias); break;
@@ -699,7 +779,7 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
   p.taps = taps; p.ksize = d->ksize; p.pad = pad; p.stride = d->stride;
   p.Cin = d->Cin; p.cin_off = d->cin_off; p.cin_group_stride = d->cin_group_stride; p.k_chunks = d->Cin / BK;
   p.bias = d->bias; p.out = d->out; p.out_planes = d->out_planes; p.out_plane_stride = d->out_plane_stride;
-  p.W_out = W_out; p.Cout_total = d->Cout_total; p.cout_off = d->cout_off;
+  p.W_out = W_out; p.Cout_total = d->Cout_total; p.cout_off = d->cout_off; p.Cout = d->Cout;
   p.cout_group_stride = d->cout_group_stride; p.act = d->act; p.out_fp32 = d->out_fp32;
   p.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
   {  // stages per accumulation chain: a stage issues 2*NX hi*hi MMAs

@@ -1,26 +1,40 @@
-// himo_b200/csrc/nn.cu -- H2: exact bidirectional 1-NN (Chamfer correspondence) on a uniform cell grid.
+// himo_b200/csrc/nn.cu -- H2: exact bidirectional 1-NN (Chamfer correspondence) on an implicit Morton octree.
 //
 // Drop-in, at the C ABI, for chamfer3D.forward / chamfer3D.backward
 // (OSF/assets/cuda/chamfer3D/chamfer3D_cuda.cpp:18-35, chamfer3D.cu:33-154).
 // The reference streams the whole other cloud past every query (O(N0*N1), 256-point smem tiles).
-// Here both clouds are counting-sorted into a shared uniform grid (one occupancy bit per cell +
-// popcount ranks => CSR cell ranges, no hash collisions to resolve) and every query expands
-// Chebyshev rings of cells until the ring bound proves the current best is the global one.  The
-// result is the *exact* nearest neighbour with the reference's tie rule (lowest index), and the
+// Here both clouds are counting-sorted by the Morton key of a uniform cell grid: one occupancy bit per
+// cell + popcount ranks give CSR cell ranges with no hashing and no radix sort, and because the key is a
+// Morton code every aligned 2^k-cell cube (an octree node) is ONE contiguous key range, i.e. one contiguous
+// run of sorted points, found with two rank lookups.  A query first looks at the 3x3x3 cells around it,
+// then at the 3x3x3 nodes of every coarser level until the covered slab proves the best candidate global;
+// nodes holding many points are descended depth-first, nearest child first, with box-distance pruning.
+// Lidar clouds span 400 m with a few far returns: the grid covers a robust box (mean +- 4 sigma, clipped
+// to the bounding box) and points outside are stored in the boundary cells -- projection onto a convex box
+// is non-expansive, so every box bound computed from the clamped query stays a valid lower bound.
+// The result is the *exact* nearest neighbour with the reference's tie rule (lowest index), and the
 // squared distance is evaluated with the reference's rounding sequence fma(dz,dz,fma(dy,dy,dx*dx)).
 #include "common.cuh"
 #include "himo_b200.h"
 
 namespace himo {
 
-constexpr long long kNNMaxCells = 1ll << 24;              // occupancy bitmap: 2 MiB per cloud
-constexpr long long kNNMaxWords = kNNMaxCells / 32 + 1;
+constexpr int kNNMaxBits = 26;                                   // key space: 2^26 cells = 8 MiB bitmap per cloud
+constexpr long long kNNMaxWords = (1ll << kNNMaxBits) / 64 + 1;  // 64-bit words (+1 so rank(n_cells) exists)
+constexpr int kNNLeaf = 32;                                      // nodes with <= this many points are scanned
 
 struct NNGrid {
-  float ox, oy, oz;   // grid origin (bbox min of both clouds)
-  float h;            // cell edge
-  int nx, ny, nz;
-  int n_words;        // ceil(nx*ny*nz/32) + 1
+  float ox, oy, oz;   // grid origin
+  float h;            // fine cell edge
+  float eps;          // slack that absorbs fp32 rounding of the cell assignment
+  int bxy, bz;        // bits per axis: x and y share bxy, bz <= bxy
+  int n_words;        // 64-bit bitmap words in use
+};
+
+struct NNStats {      // accumulated over both clouds (finite points only)
+  double sum[3], sumsq[3];
+  unsigned long long count;
+  unsigned lo[3], hi[3];   // order-preserving uint encodings of the min / max coordinates
 };
 
 // monotone float <-> uint mapping for atomicMin/atomicMax on floats
@@ -32,86 +46,178 @@ __device__ __forceinline__ float ord2f(unsigned u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-__global__ void k_nn_bbox_init(unsigned* bbox) {
-  if (threadIdx.x < 3) bbox[threadIdx.x] = 0xffffffffu;
-  else if (threadIdx.x < 6) bbox[threadIdx.x] = 0u;
+__global__ void k_nn_stats_init(NNStats* st) {
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 3; ++k) { st->sum[k] = 0.0; st->sumsq[k] = 0.0; st->lo[k] = 0xffffffffu; st->hi[k] = 0u; }
+    st->count = 0ull;
+  }
 }
 
 __global__ void __launch_bounds__(256)
-k_nn_bbox(const float* __restrict__ pc0, int n0, const float* __restrict__ pc1, int n1,
-          unsigned* __restrict__ bbox) {
+k_nn_stats(const float* __restrict__ pc0, int n0, const float* __restrict__ pc1, int n1, NNStats* __restrict__ st) {
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  double sm[3] = {0.0, 0.0, 0.0}, sq[3] = {0.0, 0.0, 0.0};
+  unsigned cnt = 0;
   const int n = n0 + n1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float* p = i < n0 ? pc0 + 3 * (size_t)i : pc1 + 3 * (size_t)(i - n0);
+    const float v[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+    if (!(isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]))) continue;
+    ++cnt;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      float v = __ldg(p + k);
-      lo[k] = fminf(lo[k], v);
-      hi[k] = fmaxf(hi[k], v);
+      lo[k] = fminf(lo[k], v[k]); hi[k] = fmaxf(hi[k], v[k]);
+      sm[k] += (double)v[k]; sq[k] += (double)v[k] * (double)v[k];
     }
   }
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
+  for (int d = 16; d > 0; d >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
+    for (int k = 0; k < 3; ++k) {
       lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], d));
       hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], d));
+      sm[k] += __shfl_xor_sync(0xffffffffu, sm[k], d);
+      sq[k] += __shfl_xor_sync(0xffffffffu, sq[k], d);
     }
   }
-  if ((threadIdx.x & 31) == 0) {
+  if ((threadIdx.x & 31) == 0 && cnt) {
+    atomicAdd(&st->count, (unsigned long long)cnt);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      if (lo[k] <= hi[k]) {
-        atomicMin(bbox + k, f2ord(lo[k]));
-        atomicMax(bbox + 3 + k, f2ord(hi[k]));
-      }
+      atomicMin(&st->lo[k], f2ord(lo[k])); atomicMax(&st->hi[k], f2ord(hi[k]));
+      atomicAdd(&st->sum[k], sm[k]); atomicAdd(&st->sumsq[k], sq[k]);
     }
   }
 }
 
-__global__ void k_nn_params(const unsigned* __restrict__ bbox, float cell, NNGrid* __restrict__ g) {
+__device__ __forceinline__ int ceil_log2_i(long long v) {
+  int b = 0;
+  while ((1ll << b) < v) ++b;
+  return b;
+}
+
+// grid = robust box (mean +- 4 sigma clipped to the bounding box), cell edge doubled until the Morton key
+// space 2^(2*bxy + bz) fits the bitmap
+__global__ void k_nn_params(const NNStats* __restrict__ st, float cell, NNGrid* __restrict__ g) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  float lo[3], hi[3];
-  for (int k = 0; k < 3; ++k) { lo[k] = ord2f(bbox[k]); hi[k] = ord2f(bbox[3 + k]); }
-  for (int k = 0; k < 3; ++k)
-    if (!(lo[k] <= hi[k]) || !isfinite(lo[k]) || !isfinite(hi[k])) { lo[k] = 0.f; hi[k] = 0.f; }
+  float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
+  float amax = 0.f;
+  if (st->count) {
+    const double n = (double)st->count;
+    for (int k = 0; k < 3; ++k) {
+      const float bl = ord2f(st->lo[k]), bh = ord2f(st->hi[k]);
+      const double mean = st->sum[k] / n;
+      double var = st->sumsq[k] / n - mean * mean;
+      const double sd = var > 0.0 ? sqrt(var) : 0.0;
+      lo[k] = fmaxf(bl, (float)(mean - 4.0 * sd));
+      hi[k] = fminf(bh, (float)(mean + 4.0 * sd));
+      if (!(hi[k] >= lo[k])) { lo[k] = bl; hi[k] = bl; }
+      amax = fmaxf(amax, fmaxf(fabsf(bl), fabsf(bh)));
+    }
+  }
   float h = cell;
-  int nx, ny, nz;
+  int bxy = 0, bz = 0;
   for (int it = 0; it < 64; ++it) {
-    nx = (int)fminf(floorf((hi[0] - lo[0]) / h) + 1.f, 2.0e9f);
-    ny = (int)fminf(floorf((hi[1] - lo[1]) / h) + 1.f, 2.0e9f);
-    nz = (int)fminf(floorf((hi[2] - lo[2]) / h) + 1.f, 2.0e9f);
-    double cells = (double)nx * (double)ny * (double)nz;
-    if (cells <= (double)kNNMaxCells) break;
-    h *= 1.26f;  // ~ cube root of 2: halve the cell count per step
+    const long long cx = (long long)fminf(floorf((hi[0] - lo[0]) / h) + 1.f, 1.0e9f);
+    const long long cy = (long long)fminf(floorf((hi[1] - lo[1]) / h) + 1.f, 1.0e9f);
+    const long long cz = (long long)fminf(floorf((hi[2] - lo[2]) / h) + 1.f, 1.0e9f);
+    bxy = ceil_log2_i(cx > cy ? cx : cy);
+    bz = ceil_log2_i(cz);
+    if (bz > bxy) bxy = bz;
+    if (2 * bxy + bz <= kNNMaxBits && bxy <= 13 && bz <= 10) break;
+    h *= 2.f;
   }
   g->ox = lo[0]; g->oy = lo[1]; g->oz = lo[2];
   g->h = h;
-  g->nx = nx; g->ny = ny; g->nz = nz;
-  long long cells = (long long)nx * ny * nz;
-  g->n_words = (int)((cells + 31) / 32 + 1);
+  g->eps = 1e-3f * h + 8.f * 1.2e-7f * amax;
+  g->bxy = bxy; g->bz = bz;
+  g->n_words = (int)(((1ll << (2 * bxy + bz)) >> 6) + 1);
 }
 
-__device__ __forceinline__ void nn_cell(const NNGrid& g, float x, float y, float z, int& cx, int& cy,
-                                        int& cz) {
-  cx = min(max(__float2int_rd(__fdiv_rn(x - g.ox, g.h)), 0), g.nx - 1);
-  cy = min(max(__float2int_rd(__fdiv_rn(y - g.oy, g.h)), 0), g.ny - 1);
-  cz = min(max(__float2int_rd(__fdiv_rn(z - g.oz, g.h)), 0), g.nz - 1);
+// ---- Morton key with unequal bit counts: the low bz levels interleave (x,y,z), the upper bxy-bz levels (x,y)
+__device__ __forceinline__ unsigned part1by2(unsigned x) {   // 10 bits -> every third bit
+  x &= 0x3ffu;
+  x = (x | (x << 16)) & 0x030000FFu;
+  x = (x | (x << 8)) & 0x0300F00Fu;
+  x = (x | (x << 4)) & 0x030C30C3u;
+  x = (x | (x << 2)) & 0x09249249u;
+  return x;
+}
+__device__ __forceinline__ unsigned part1by1(unsigned x) {   // 16 bits -> every second bit
+  x &= 0xffffu;
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+__device__ __forceinline__ unsigned compact1by2(unsigned x) {
+  x &= 0x09249249u;
+  x = (x ^ (x >> 2)) & 0x030C30C3u;
+  x = (x ^ (x >> 4)) & 0x0300F00Fu;
+  x = (x ^ (x >> 8)) & 0x030000FFu;
+  x = (x ^ (x >> 16)) & 0x3ffu;
+  return x;
+}
+__device__ __forceinline__ unsigned compact1by1(unsigned x) {
+  x &= 0x55555555u;
+  x = (x ^ (x >> 1)) & 0x33333333u;
+  x = (x ^ (x >> 2)) & 0x0F0F0F0Fu;
+  x = (x ^ (x >> 4)) & 0x00FF00FFu;
+  x = (x ^ (x >> 8)) & 0xffffu;
+  return x;
+}
+// dilated x component (y: shift the result left by 1; z: part1by2(cz) << 2)
+__device__ __forceinline__ unsigned dil_xy(unsigned c, int bz) {
+  const unsigned lowmask = (1u << bz) - 1u;
+  return part1by2(c & lowmask) | (part1by1(c >> bz) << (3 * bz));
+}
+__device__ __forceinline__ unsigned nn_key(const NNGrid& g, int cx, int cy, int cz) {
+  return dil_xy((unsigned)cx, g.bz) | (dil_xy((unsigned)cy, g.bz) << 1) | (part1by2((unsigned)cz) << 2);
+}
+__device__ __forceinline__ void nn_unkey(const NNGrid& g, unsigned key, int& cx, int& cy, int& cz) {
+  const unsigned low = key & ((1u << (3 * g.bz)) - 1u), high = key >> (3 * g.bz);
+  cx = (int)(compact1by2(low) | (compact1by1(high) << g.bz));
+  cy = (int)(compact1by2(low >> 1) | (compact1by1(high >> 1) << g.bz));
+  cz = (int)compact1by2(low >> 2);
+}
+
+// cell of a point; points outside the grid (or non-finite) land in the nearest boundary cell
+__device__ __forceinline__ void nn_cell(const NNGrid& g, float x, float y, float z, int& cx, int& cy, int& cz) {
+  const int nxy = (1 << g.bxy) - 1, nz = (1 << g.bz) - 1;
+  cx = min(max(__float2int_rd(__fdiv_rn(x - g.ox, g.h)), 0), nxy);
+  cy = min(max(__float2int_rd(__fdiv_rn(y - g.oy, g.h)), 0), nxy);
+  cz = min(max(__float2int_rd(__fdiv_rn(z - g.oz, g.h)), 0), nz);
 }
 
 struct NNCloud {
-  const float* pts;      // [n,3]
+  const float* pts;              // [n,3]
   int n;
-  int* keys;             // [n]
-  unsigned* bitmap;      // [kNNMaxWords]
-  int* word_prefix;      // [kNNMaxWords]
-  int* count;            // [n+1] zeroed
-  int* slot;             // [n]
-  int* cell_start;       // [n+2]
-  float4* sorted;        // [n] xyz + original index bits
-  int* n_cells_occ;      // [1]
+  unsigned* keys;                // [n] Morton key, then occupied-cell rank
+  unsigned long long* bitmap;    // [kNNMaxWords]
+  int* word_prefix;              // [kNNMaxWords]
+  int* count;                    // [n+1] zeroed
+  int* slot;                     // [n]
+  int* cell_start;               // [n+2]
+  float4* sorted;                // [n] xyz + original index bits
+  int* n_cells_occ;              // [1]
 };
+
+__device__ __forceinline__ int nn_rank(const unsigned long long* __restrict__ bitmap, const int* __restrict__ prefix,
+                                       unsigned key) {
+  const unsigned w = key >> 6;
+  const unsigned long long below = (1ull << (key & 63u)) - 1ull;
+  return __ldg(prefix + w) + __popcll(__ldg(bitmap + w) & below);
+}
+
+__global__ void __launch_bounds__(256)
+k_nn_clear(NNCloud c0, NNCloud c1, const NNGrid* __restrict__ gp) {
+  const int nw = gp->n_words;
+  const NNCloud& c = blockIdx.y == 0 ? c0 : c1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += gridDim.x * blockDim.x) c.bitmap[i] = 0ull;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= c.n; i += gridDim.x * blockDim.x) c.count[i] = 0;
+}
 
 __global__ void __launch_bounds__(256)
 k_nn_mark(NNCloud c0, NNCloud c1, const NNGrid* __restrict__ gp) {
@@ -121,19 +227,23 @@ k_nn_mark(NNCloud c0, NNCloud c1, const NNGrid* __restrict__ gp) {
     int cx, cy, cz;
     nn_cell(g, __ldg(c.pts + 3 * (size_t)i), __ldg(c.pts + 3 * (size_t)i + 1),
             __ldg(c.pts + 3 * (size_t)i + 2), cx, cy, cz);
-    int key = (cz * g.ny + cy) * g.nx + cx;
+    const unsigned key = nn_key(g, cx, cy, cz);
     c.keys[i] = key;
-    atomicOr(c.bitmap + (key >> 5), 1u << (key & 31));
+    atomicOr(c.bitmap + (key >> 6), 1ull << (key & 63u));
   }
 }
+
+struct MapPopc64 {
+  const unsigned long long* p;
+  __device__ int operator()(int i) const { return __popcll(p[i]); }
+};
 
 __global__ void __launch_bounds__(256)
 k_nn_rank(NNCloud c0, NNCloud c1) {
   const NNCloud& c = blockIdx.y == 0 ? c0 : c1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
-    int key = c.keys[i];
-    int rank = bitmap_rank_lb(c.bitmap, c.word_prefix, key);
-    c.keys[i] = rank;  // keys now hold the occupied-cell rank
+    const int rank = nn_rank(c.bitmap, c.word_prefix, c.keys[i]);
+    c.keys[i] = (unsigned)rank;  // keys now hold the occupied-cell rank
     c.slot[i] = atomicAdd(c.count + rank, 1);
   }
 }
@@ -142,77 +252,177 @@ __global__ void __launch_bounds__(256)
 k_nn_fill(NNCloud c0, NNCloud c1) {
   const NNCloud& c = blockIdx.y == 0 ? c0 : c1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
-    int pos = c.cell_start[c.keys[i]] + c.slot[i];
+    const int pos = c.cell_start[c.keys[i]] + c.slot[i];
     c.sorted[pos] = make_float4(__ldg(c.pts + 3 * (size_t)i), __ldg(c.pts + 3 * (size_t)i + 1),
                                 __ldg(c.pts + 3 * (size_t)i + 2), __int_as_float(i));
   }
 }
 
-// One thread per query, queries taken in cell-sorted order so that the lanes of a warp walk the
-// same reference ranges (L1 broadcast).  Both directions run in one launch (blockIdx.y).
+// ---- search ---------------------------------------------------------------------------------------------
+struct NNQuery {
+  float x, y, z;        // the query
+  float px, py, pz;     // the query projected onto the grid box (all box bounds use this)
+  float best;
+  int best_i;
+};
+
+__device__ __forceinline__ void nn_scan(const float4* __restrict__ rs, int s, int e, NNQuery& q) {
+  for (int j = s; j < e; ++j) {
+    const float4 c = __ldg(rs + j);
+    const float dx = c.x - q.x, dy = c.y - q.y, dz = c.z - q.z;
+    const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    const int ci = __float_as_int(c.w);
+    if (d < q.best || (d == q.best && ci < q.best_i)) { q.best = d; q.best_i = ci; }
+  }
+}
+
+// squared distance from the projected query to the level-`lvl` node with node coordinates (bx,by,bz_), shrunk by eps
+__device__ __forceinline__ float nn_box_d2(const NNGrid& g, const NNQuery& q, int lvl, int bx, int by, int bz_) {
+  const float H = g.h * (float)(1 << lvl);
+  const float lx = g.ox + (float)bx * H, ly = g.oy + (float)by * H, lz = g.oz + (float)bz_ * H;
+  const float dx = fmaxf(fmaxf(lx - q.px, q.px - (lx + H)) - g.eps, 0.f);
+  const float dy = fmaxf(fmaxf(ly - q.py, q.py - (ly + H)) - g.eps, 0.f);
+  const float dz = fmaxf(fmaxf(lz - q.pz, q.pz - (lz + H)) - g.eps, 0.f);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+__device__ __forceinline__ int nn_level_bits(const NNGrid& g, int lvl) {
+  return 2 * min(lvl, g.bxy) + min(lvl, g.bz);
+}
+
+struct NNRef {
+  const unsigned long long* __restrict__ bitmap;
+  const int* __restrict__ prefix;
+  const int* __restrict__ cstart;
+  const float4* __restrict__ rs;
+};
+
+// point range of the node whose first key is `base` (level lvl)
+__device__ __forceinline__ void nn_node_range(const NNGrid& g, const NNRef& r, unsigned base, int lvl, int& s, int& e) {
+  const unsigned size = 1u << nn_level_bits(g, lvl);
+  s = __ldg(r.cstart + nn_rank(r.bitmap, r.prefix, base));
+  e = __ldg(r.cstart + nn_rank(r.bitmap, r.prefix, base + size));
+}
+
+// depth-first descent of one node, nearest child first, pruned by the current best
+__device__ void nn_descend(const NNGrid& g, const NNRef& r, NNQuery& q, int qcx, int qcy, int qcz, unsigned base0,
+                           int lvl0) {
+  unsigned stack[96];
+  int sp = 0;
+  stack[sp++] = base0 | ((unsigned)lvl0 << 27);
+  while (sp > 0) {
+    const unsigned ent = stack[--sp];
+    const unsigned base = ent & ((1u << 27) - 1u);
+    const int lvl = (int)(ent >> 27);
+    int cx, cy, cz;
+    nn_unkey(g, base, cx, cy, cz);
+    if (nn_box_d2(g, q, lvl, cx >> lvl, lvl < g.bxy ? cy >> lvl : 0, lvl < g.bz ? cz >> lvl : 0) > q.best) continue;
+    int s, e;
+    nn_node_range(g, r, base, lvl, s, e);
+    if (s == e) continue;
+    if (e - s <= kNNLeaf || lvl == 0) { nn_scan(r.rs, s, e, q); continue; }
+    // children at level lvl-1: an axis splits when it still has a bit at that level
+    const int cl = lvl - 1;
+    const bool sxy = cl < g.bxy, sz = cl < g.bz;
+    const int nx_ = sxy ? (((qcx >> cl) > ((cx >> cl) & ~1)) ? 1 : 0) : 0;   // nearer half per axis
+    const int ny_ = sxy ? (((qcy >> cl) > ((cy >> cl) & ~1)) ? 1 : 0) : 0;
+    const int nz_ = sz ? (((qcz >> cl) > ((cz >> cl) & ~1)) ? 1 : 0) : 0;
+    const int nchild = (sxy ? 4 : 1) * (sz ? 2 : 1);
+    // pushed farthest-first so that the nearest child is popped first
+    for (int m = nchild - 1; m >= 0; --m) {
+      int ix = 0, iy = 0, iz = 0, mm = m;
+      if (sxy) { ix = (mm & 1) ^ nx_; iy = ((mm >> 1) & 1) ^ ny_; mm >>= 2; }
+      if (sz) iz = (mm & 1) ^ nz_;
+      const int ccx = cx | (ix << cl), ccy = cy | (iy << cl), ccz = cz | (iz << cl);
+      if (nn_box_d2(g, q, cl, ccx >> cl, cl < g.bxy ? ccy >> cl : 0, cl < g.bz ? ccz >> cl : 0) > q.best) continue;
+      if (sp < 96) stack[sp++] = nn_key(g, ccx, ccy, ccz) | ((unsigned)cl << 27);
+      else {   // cannot happen (depth <= 13, <= 7 pending siblings per level); scan rather than drop
+        int cs, ce;
+        nn_node_range(g, r, nn_key(g, ccx, ccy, ccz), cl, cs, ce);
+        nn_scan(r.rs, cs, ce, q);
+      }
+    }
+  }
+}
+
+// One thread per query, queries taken in Morton order so that the lanes of a warp walk the same nodes.
+// Both directions run in one launch (blockIdx.y).  radius2: +inf, or the squared search radius.
 __global__ void __launch_bounds__(128)
 k_nn_search(NNCloud c0, NNCloud c1, const NNGrid* __restrict__ gp, float* __restrict__ dist0,
-            int32_t* __restrict__ idx0, float* __restrict__ dist1, int32_t* __restrict__ idx1) {
+            int32_t* __restrict__ idx0, float* __restrict__ dist1, int32_t* __restrict__ idx1, float radius2) {
   const NNGrid g = *gp;
-  const NNCloud& q = blockIdx.y == 0 ? c0 : c1;
-  const NNCloud& r = blockIdx.y == 0 ? c1 : c0;
+  const NNCloud& qc = blockIdx.y == 0 ? c0 : c1;
+  const NNCloud& rc = blockIdx.y == 0 ? c1 : c0;
   float* __restrict__ dist = blockIdx.y == 0 ? dist0 : dist1;
   int32_t* __restrict__ idx = blockIdx.y == 0 ? idx0 : idx1;
-  const unsigned* __restrict__ bitmap = r.bitmap;
-  const int* __restrict__ prefix = r.word_prefix;
-  const int* __restrict__ cstart = r.cell_start;
-  const float4* __restrict__ rs = r.sorted;
-  const int max_ring = max(g.nx, max(g.ny, g.nz));
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < q.n; t += gridDim.x * blockDim.x) {
-    const float4 p = q.sorted[t];
+  NNRef r;
+  r.bitmap = rc.bitmap; r.prefix = rc.word_prefix; r.cstart = rc.cell_start; r.rs = rc.sorted;
+  const int nxy = 1 << g.bxy, nz = 1 << g.bz;
+  const int top = g.bxy;                                   // level at which one node covers the grid
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < qc.n; t += gridDim.x * blockDim.x) {
+    const float4 p = qc.sorted[t];
+    const int qi = __float_as_int(p.w);
+    NNQuery q;
+    q.x = p.x; q.y = p.y; q.z = p.z;
+    q.best = radius2; q.best_i = -1;
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) {   // the reference's comparisons all fail on NaN
+      dist[qi] = 1e20f; idx[qi] = -1;
+      continue;
+    }
+    const float ex = g.h * (float)nxy, ez = g.h * (float)nz;
+    q.px = fminf(fmaxf(p.x, g.ox), g.ox + ex);
+    q.py = fminf(fmaxf(p.y, g.oy), g.oy + ex);
+    q.pz = fminf(fmaxf(p.z, g.oz), g.oz + ez);
     int cx, cy, cz;
     nn_cell(g, p.x, p.y, p.z, cx, cy, cz);
-    // distance from the query to the nearest face of its own cell (0 if it was clamped in)
-    float fx = p.x - (g.ox + (float)cx * g.h), fy = p.y - (g.oy + (float)cy * g.h),
-          fz = p.z - (g.oz + (float)cz * g.h);
-    float dface = fminf(fminf(fminf(fx, g.h - fx), fminf(fy, g.h - fy)), fminf(fz, g.h - fz));
-    dface = fmaxf(dface, 0.f);
-    float best = 1e20f;
-    int best_i = -1;
-    for (int ring = 0; ring <= max_ring; ++ring) {
-      const int z_lo = max(cz - ring, 0), z_hi = min(cz + ring, g.nz - 1);
-      const int y_lo = max(cy - ring, 0), y_hi = min(cy + ring, g.ny - 1);
-      for (int z = z_lo; z <= z_hi; ++z) {
-        const bool z_shell = (z == cz - ring) || (z == cz + ring);
-        for (int y = y_lo; y <= y_hi; ++y) {
-          const bool shell = z_shell || (y == cy - ring) || (y == cy + ring);
-          // on the shell take the whole x-row, inside only its two end cells
-          const int nseg = (shell || ring == 0) ? 1 : 2;
-          for (int s = 0; s < nseg; ++s) {
-            int xa, xb;
-            if (nseg == 1) { xa = cx - ring; xb = cx + ring; }
-            else { xa = xb = (s == 0 ? cx - ring : cx + ring); }
-            if (xb < 0 || xa >= g.nx) continue;
-            xa = max(xa, 0); xb = min(xb, g.nx - 1);
-            const int row = (z * g.ny + y) * g.nx;
-            const int beg = cstart[bitmap_rank_lb(bitmap, prefix, row + xa)];
-            const int end = cstart[bitmap_rank_lb(bitmap, prefix, row + xb + 1)];
-            for (int j = beg; j < end; ++j) {
-              const float4 c = rs[j];
-              const float dx = c.x - p.x, dy = c.y - p.y, dz = c.z - p.z;
-              const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-              const int ci = __float_as_int(c.w);
-              if (d < best || (d == best && ci < best_i)) { best = d; best_i = ci; }
+    for (int lvl = 0; lvl <= top; ++lvl) {
+      const float H = g.h * (float)(1 << lvl);
+      const int kx = cx >> lvl, ky = cy >> lvl, kz = lvl < g.bz ? cz >> lvl : 0;
+      const int mxy = max(nxy >> lvl, 1), mz = max(nz >> lvl, 1);
+      for (int dz = -1; dz <= 1; ++dz) {
+        const int z = kz + dz;
+        if (z < 0 || z >= mz) continue;
+        const unsigned Z = part1by2((unsigned)(z << lvl)) << 2;
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int y = ky + dy;
+          if (y < 0 || y >= mxy) continue;
+          const unsigned Y = dil_xy((unsigned)(y << lvl), g.bz) << 1;
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int x = kx + dx;
+            if (x < 0 || x >= mxy) continue;
+            if (nn_box_d2(g, q, lvl, x, y, z) > q.best) continue;
+            const unsigned base = dil_xy((unsigned)(x << lvl), g.bz) | Y | Z;
+            if (lvl == 0) {
+              const unsigned long long w = __ldg(r.bitmap + (base >> 6));
+              if (!((w >> (base & 63u)) & 1ull)) continue;
+              const int rk = __ldg(r.prefix + (base >> 6)) + __popcll(w & ((1ull << (base & 63u)) - 1ull));
+              nn_scan(r.rs, __ldg(r.cstart + rk), __ldg(r.cstart + rk + 1), q);
+            } else {
+              int s, e;
+              nn_node_range(g, r, base, lvl, s, e);
+              if (s == e) continue;
+              if (e - s <= kNNLeaf) nn_scan(r.rs, s, e, q);
+              else nn_descend(g, r, q, cx, cy, cz, base, lvl);
             }
           }
         }
       }
-      // every unexamined point lies outside ring `ring`: at least ring*h + dface away
-      // (small slack absorbs fp32 rounding in the cell assignment)
-      const float bound = (float)ring * g.h + dface - 1e-3f * g.h;
-      if (best_i >= 0 && bound > 0.f && best < bound * bound) break;
-      if (cx - ring <= 0 && cx + ring >= g.nx - 1 && cy - ring <= 0 && cy + ring >= g.ny - 1 &&
-          cz - ring <= 0 && cz + ring >= g.nz - 1)
-        break;  // whole grid examined
+      // everything stored outside the 3x3x3 slab is at least `bound` away (sides cut by the grid edge are open:
+      // nothing is stored beyond them)
+      float bound = INFINITY;
+      if (kx - 1 >= 0) bound = fminf(bound, q.px - (g.ox + (float)(kx - 1) * H));
+      if (kx + 1 < mxy) bound = fminf(bound, (g.ox + (float)(kx + 2) * H) - q.px);
+      if (ky - 1 >= 0) bound = fminf(bound, q.py - (g.oy + (float)(ky - 1) * H));
+      if (ky + 1 < mxy) bound = fminf(bound, (g.oy + (float)(ky + 2) * H) - q.py);
+      if (kz - 1 >= 0) bound = fminf(bound, q.pz - (g.oz + (float)(kz - 1) * H));
+      if (kz + 1 < mz) bound = fminf(bound, (g.oz + (float)(kz + 2) * H) - q.pz);
+      bound -= g.eps;
+      if (bound == INFINITY) break;                               // whole grid examined
+      if (bound > 0.f && q.best < bound * bound) break;
     }
-    const int qi = __float_as_int(p.w);
-    dist[qi] = best;
-    idx[qi] = best_i;
+    if (q.best_i < 0) q.best = 1e20f;                             // radius-limited search found nothing
+    dist[qi] = q.best;
+    idx[qi] = q.best_i;
   }
 }
 
@@ -243,13 +453,14 @@ k_chamfer_grad(const float* __restrict__ a, int na, const float* __restrict__ b,
 static size_t nn_cloud_bytes(int n) {
   size_t m = (size_t)(n > 0 ? n : 1);
   size_t b = 0;
-  b += align_up(m * sizeof(int), 256);                    // keys
-  b += align_up((size_t)kNNMaxWords * 4, 256) * 2;         // bitmap + prefix
-  b += align_up((m + 1) * sizeof(int), 256);              // count
-  b += align_up(m * sizeof(int), 256);                    // slot
-  b += align_up((m + 2) * sizeof(int), 256);              // cell_start
-  b += align_up(m * sizeof(float4), 256);                 // sorted
-  b += 256;                                               // n_cells_occ
+  b += align_up(m * sizeof(unsigned), 256);                       // keys
+  b += align_up((size_t)kNNMaxWords * sizeof(unsigned long long), 256);   // bitmap
+  b += align_up((size_t)kNNMaxWords * sizeof(int), 256);          // word prefix
+  b += align_up((m + 1) * sizeof(int), 256);                      // count
+  b += align_up(m * sizeof(int), 256);                            // slot
+  b += align_up((m + 2) * sizeof(int), 256);                      // cell_start
+  b += align_up(m * sizeof(float4), 256);                         // sorted
+  b += 256;                                                       // n_cells_occ
   b += ScanScratch::bytes(kNNMaxWords) + ScanScratch::bytes((long long)m + 2);
   return b;
 }
@@ -263,9 +474,9 @@ extern "C" size_t himo_chamfer_workspace_bytes(int n0, int n1) {
   return nn_cloud_bytes(n0) + nn_cloud_bytes(n1) + 4096 + 16 * 256;
 }
 
-extern "C" int himo_chamfer_forward(const float* pc0, int n0, const float* pc1, int n1, float* dist0,
-                                    float* dist1, int32_t* idx0, int32_t* idx1, float cell_size,
-                                    void* workspace, size_t workspace_bytes, void* stream_) {
+static int nn_forward_impl(const float* pc0, int n0, const float* pc1, int n1, float* dist0,
+                           float* dist1, int32_t* idx0, int32_t* idx1, float cell_size, float radius2,
+                           void* workspace, size_t workspace_bytes, void* stream_) {
   if (n0 < 0 || n1 < 0) return HIMO_ERR_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
   if ((n0 > 0 && (!pc0 || !dist0 || !idx0)) || (n1 > 0 && (!pc1 || !dist1 || !idx1))) return HIMO_ERR_ARG;
@@ -275,9 +486,9 @@ extern "C" int himo_chamfer_forward(const float* pc0, int n0, const float* pc1, 
     if (n1 > 0) { k_nn_fill_empty<<<ceil_div(n1, 256), 256, 0, stream>>>(dist1, idx1, n1); HIMO_LAUNCH_RET(); }
     return HIMO_OK;
   }
-  if (!(cell_size > 0.f)) cell_size = 0.5f;
+  if (!(cell_size > 0.f)) cell_size = 0.25f;
   Arena A(workspace, workspace_bytes);
-  unsigned* bbox = A.take<unsigned>(8);
+  NNStats* stats = A.take<NNStats>(1);
   NNGrid* grid = A.take<NNGrid>(1);
   NNCloud c[2];
   char* scan_w[2];
@@ -287,8 +498,8 @@ extern "C" int himo_chamfer_forward(const float* pc0, int n0, const float* pc1, 
   for (int k = 0; k < 2; ++k) {
     c[k].pts = pts[k];
     c[k].n = ns[k];
-    c[k].keys = A.take<int>(ns[k]);
-    c[k].bitmap = A.take<unsigned>(kNNMaxWords);
+    c[k].keys = A.take<unsigned>(ns[k]);
+    c[k].bitmap = A.take<unsigned long long>(kNNMaxWords);
     c[k].word_prefix = A.take<int>(kNNMaxWords);
     c[k].count = A.take<int>((size_t)ns[k] + 1);
     c[k].slot = A.take<int>(ns[k]);
@@ -300,23 +511,20 @@ extern "C" int himo_chamfer_forward(const float* pc0, int n0, const float* pc1, 
   }
   if (!A.ok()) return HIMO_ERR_WORKSPACE;
 
-  k_nn_bbox_init<<<1, 32, 0, stream>>>(bbox);
+  k_nn_stats_init<<<1, 32, 0, stream>>>(stats);
   HIMO_LAUNCH_RET();
-  k_nn_bbox<<<min(ceil_div(n0 + n1, 256), kNumSMs * 4), 256, 0, stream>>>(pc0, n0, pc1, n1, bbox);
+  k_nn_stats<<<min(ceil_div(n0 + n1, 256), kNumSMs * 4), 256, 0, stream>>>(pc0, n0, pc1, n1, stats);
   HIMO_LAUNCH_RET();
-  k_nn_params<<<1, 32, 0, stream>>>(bbox, cell_size, grid);
+  k_nn_params<<<1, 32, 0, stream>>>(stats, cell_size, grid);
   HIMO_LAUNCH_RET();
-  for (int k = 0; k < 2; ++k) {
-    // the bitmap only needs clearing up to n_words, which is device-side; clear the cap (2 MiB)
-    HIMO_CUDA_RET(cudaMemsetAsync(c[k].bitmap, 0, (size_t)kNNMaxWords * 4, stream));
-    HIMO_CUDA_RET(cudaMemsetAsync(c[k].count, 0, ((size_t)ns[k] + 1) * sizeof(int), stream));
-  }
   const int nmax = n0 > n1 ? n0 : n1;
   dim3 grid2(min(ceil_div(nmax, 256), kNumSMs * 8), 2);
+  k_nn_clear<<<dim3(kNumSMs * 4, 2), 256, 0, stream>>>(c[0], c[1], grid);   // n_words is device-side
+  HIMO_LAUNCH_RET();
   k_nn_mark<<<grid2, 256, 0, stream>>>(c[0], c[1], grid);
   HIMO_LAUNCH_RET();
   for (int k = 0; k < 2; ++k)
-    HIMO_CUDA_RET(scan_exclusive(MapPopc{c[k].bitmap}, c[k].word_prefix, (int)kNNMaxWords,
+    HIMO_CUDA_RET(scan_exclusive(MapPopc64{c[k].bitmap}, c[k].word_prefix, (int)kNNMaxWords,
                                  &grid->n_words, c[k].n_cells_occ, scan_w[k], stream));
   k_nn_rank<<<grid2, 256, 0, stream>>>(c[0], c[1]);
   HIMO_LAUNCH_RET();
@@ -326,9 +534,26 @@ extern "C" int himo_chamfer_forward(const float* pc0, int n0, const float* pc1, 
   k_nn_fill<<<grid2, 256, 0, stream>>>(c[0], c[1]);
   HIMO_LAUNCH_RET();
   dim3 grid3(ceil_div(nmax, 128), 2);
-  k_nn_search<<<grid3, 128, 0, stream>>>(c[0], c[1], grid, dist0, idx0, dist1, idx1);
+  k_nn_search<<<grid3, 128, 0, stream>>>(c[0], c[1], grid, dist0, idx0, dist1, idx1, radius2);
   HIMO_LAUNCH_RET();
   return HIMO_OK;
+}
+
+extern "C" int himo_chamfer_forward(const float* pc0, int n0, const float* pc1, int n1, float* dist0,
+                                    float* dist1, int32_t* idx0, int32_t* idx1, float cell_size,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  return nn_forward_impl(pc0, n0, pc1, n1, dist0, dist1, idx0, idx1, cell_size, INFINITY, workspace,
+                         workspace_bytes, stream);
+}
+
+extern "C" int himo_chamfer_forward_radius(const float* pc0, int n0, const float* pc1, int n1, float* dist0,
+                                           float* dist1, int32_t* idx0, int32_t* idx1, float radius,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (!(radius > 0.f)) return HIMO_ERR_ARG;
+  // candidates are accepted on d < best: start just above r^2 so that d == r^2 still counts
+  const float r2 = nextafterf(radius * radius, INFINITY);
+  return nn_forward_impl(pc0, n0, pc1, n1, dist0, dist1, idx0, idx1, 0.f, r2, workspace,
+                         workspace_bytes, stream);
 }
 
 extern "C" int himo_chamfer_backward(const float* pc0, int n0, const float* pc1, int n1,

@@ -83,6 +83,14 @@ size_t himo_chamfer_workspace_bytes(int n0, int n1);
 int himo_chamfer_forward(const float* pc0, int n0, const float* pc1, int n1, float* dist0,
                          float* dist1, int32_t* idx0, int32_t* idx1, float cell_size,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* Radius-limited form of the same search (the "grid-radius KNN" of the north star): the exact nearest
+ * neighbour when it lies within `radius` metres (dist^2 <= radius^2), otherwise (1e20, -1).  Serves the
+ * reference's truncated consumers without searching past the truncation: nnChamferDis.truncated_dis
+ * zeroes d^2 >= 2 (OSF/assets/cuda/chamfer3D/__init__.py:77-82), SeFlow's TRUNCATED_DIST = 4
+ * (OSF/src/lossfuncs/selfsupervise.py:23), the nnd auto-label keeps d < 4.4 m (OSF/process.py:124). */
+int himo_chamfer_forward_radius(const float* pc0, int n0, const float* pc1, int n1, float* dist0,
+                                float* dist1, int32_t* idx0, int32_t* idx1, float radius,
+                                void* workspace, size_t workspace_bytes, void* stream);
 /* replaces: chamfer3D.backward(pc0, pc1, idx0, idx1, grad_dist0, grad_dist1, grad_pc0, grad_pc1)
  *           OSF/assets/cuda/chamfer3D/chamfer3D.cu:107-154.  grad_pc0/grad_pc1 are accumulated
  *           into (the caller pre-zeroes them, as chamfer3D/__init__.py:44-45 does). */

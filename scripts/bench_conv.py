@@ -4,17 +4,21 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from himo_b200 import conv, _lib
 
-LAYERS = [  # name, H, W, Cin, Cout, ksize, stride, groups
-    ("enc1.1 64->64 @256 x3", 256, 256, 64, 64, 3, 1, 3),
-    ("enc2.1 128->128 @128 x3", 128, 128, 128, 128, 3, 1, 3),
-    ("enc3.1 256->256 @64 x3", 64, 64, 256, 256, 3, 1, 3),
-    ("b1.u3 1x1 384->384 @128", 128, 128, 384, 384, 1, 1, 1),
-    ("b1.u4 768->384 @128", 128, 128, 768, 384, 3, 1, 1),
-    ("b2.u4 384->192 @256", 256, 256, 384, 192, 3, 1, 1),
-    ("b3.u4 192->96 @512", 512, 512, 192, 96, 3, 1, 1),
-    ("b3.u5 96->96 @512", 512, 512, 96, 96, 3, 1, 1),
-    ("gru zr 288->384 x100k", 782, 128, 288, 384, 1, 1, 1),
+LAYERS = [  # name, H, W, Cin, Cout, ksize, stride, groups, act (1 = bias + GELU, as the encoder), fp32 out
+    ("enc1.0 32->64 s2 @512 x3", 512, 512, 32, 64, 3, 2, 3, 1, 0),
+    ("enc1.1 64->64 @256 x3", 256, 256, 64, 64, 3, 1, 3, 1, 0),
+    ("enc2.1 128->128 @128 x3", 128, 128, 128, 128, 3, 1, 3, 1, 0),
+    ("enc3.1 256->256 @64 x3", 64, 64, 256, 256, 3, 1, 3, 1, 0),
+    ("b1.u3 1x1 384->384 @128", 128, 128, 384, 384, 1, 1, 1, 0, 0),
+    ("b1.u4 768->384 @128", 128, 128, 768, 384, 3, 1, 1, 0, 0),
+    ("b2.u4 384->192 @256", 256, 256, 384, 192, 3, 1, 1, 0, 0),
+    ("b3.u4 192->96 @512", 512, 512, 192, 96, 3, 1, 1, 0, 0),
+    ("b3.u5 96->96 @512", 512, 512, 96, 96, 3, 1, 1, 0, 0),
+    ("gru zr 288->384 x100k", 782, 128, 288, 384, 1, 1, 1, 2, 1),
+    ("gru q 288->192 x100k", 782, 128, 288, 192, 1, 1, 1, 3, 1),
 ]
+WARM = int(os.environ.get("WARM", "3"))
+REPS = int(os.environ.get("REPS", "20"))
 planes = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 sel = sys.argv[2] if len(sys.argv) > 2 else ""
 L = _lib.lib()
@@ -26,7 +30,7 @@ if os.environ.get("HALO") is not None:
     L.himo_conv_set_halo(int(os.environ["HALO"]))
 if os.environ.get("FLUSH") is not None:
     L.himo_conv_set_flush_iters(int(os.environ["FLUSH"]))
-for name, H, W, cin, cout, k, s, g in LAYERS:
+for name, H, W, cin, cout, k, s, g, act, f32 in LAYERS:
     if sel and sel not in name:
         continue
     x = torch.randn(H, W, g * cin, device="cuda")
@@ -35,15 +39,17 @@ for name, H, W, cin, cout, k, s, g in LAYERS:
     ws = conv.weight_prescale(w, planes)
     wp = conv.pack_conv_weight(w, planes, ws).cuda()
     Ho, Wo = H // s, W // s
-    out = torch.zeros((planes, Ho, Wo, g * cout), dtype=torch.bfloat16, device="cuda")
+    out = (torch.zeros((Ho, Wo, g * cout), device="cuda") if f32 else
+           torch.zeros((planes, Ho, Wo, g * cout), dtype=torch.bfloat16, device="cuda"))
+    bias = torch.randn(cout, device="cuda") * 0.1 if act else None
     def run():
-        conv.conv2d_nhwc(xp, wp, None, out, ksize=k, stride=s, cin=cin, n_groups=g, cin_group_stride=cin if g > 1 else 0,
+        conv.conv2d_nhwc(xp, wp, bias, out, ksize=k, act=act, stride=s, cin=cin, n_groups=g, cin_group_stride=cin if g > 1 else 0,
                          cout_group_stride=cout if g > 1 else 0, acc_scale=1.0 / ws)
-    for _ in range(3):
+    for _ in range(WARM):
         run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 20
+    reps = REPS
     e0.record()
     for _ in range(reps):
         run()

@@ -163,3 +163,29 @@ def test_chamfer_empty_and_backward():
     ra, rb = leaf.chamfer_backward(a, b, i0, i1, g0, g1)
     np.testing.assert_allclose(ga.cpu().numpy(), ra, rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(gb.cpu().numpy(), rb, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("radius", [0.5, 1.0, 1.414, 2.0, 4.4])
+@pytest.mark.parametrize("kind", ["uniform", "lidar"])
+def test_chamfer_radius_matches_truncated_reference(kind, radius):
+    """Radius-limited search == the reference's full search followed by its truncation mask: every point
+    whose exact squared distance is <= r^2 gets the bit-identical (dist, idx); every other point (1e20, -1)
+    (truncations used by the reference: chamfer3D/__init__.py:64-82, selfsupervise.py:23, process.py:124)."""
+    if kind == "uniform":
+        a, b = frames.uniform_frame(6000, 31), frames.uniform_frame(5000, 32)
+    else:
+        tr = frames.lidar_triple(8000, 33)
+        a, b = tr["pc0"], tr["pc1"]
+    r0, r1, j0, j1 = leaf.chamfer_forward(a, b)
+    pa, pb = torch.from_numpy(a).cuda().contiguous(), torch.from_numpy(b).cuda().contiguous()
+    d0 = torch.zeros(a.shape[0], device="cuda"); d1 = torch.zeros(b.shape[0], device="cuda")
+    i0 = torch.zeros(a.shape[0], dtype=torch.int32, device="cuda")
+    i1 = torch.zeros(b.shape[0], dtype=torch.int32, device="cuda")
+    assert chamfer3d_ext.forward_radius(pa, pb, d0, d1, i0, i1, radius) == 1
+    r2 = np.float32(radius) * np.float32(radius)
+    for ref_d, ref_i, got_d, got_i in ((r0, j0, d0, i0), (r1, j1, d1, i1)):
+        keep = ref_d <= r2
+        exp_d = np.where(keep, ref_d, np.float32(1e20))
+        exp_i = np.where(keep, ref_i, -1)
+        assert (got_d.cpu().numpy() == exp_d).all() and (got_i.cpu().numpy() == exp_i).all()
+    assert 0 < keep.sum()
