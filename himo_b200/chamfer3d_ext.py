@@ -3,13 +3,14 @@
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
 from . import _lib
 
-#: search-cell edge in metres used by forward(); <=0 selects the library default (0.5 m)
-CELL_SIZE = 0.0
+#: finest search-cell edge in metres used by forward(); <=0 selects the library default (0.25 m)
+CELL_SIZE = float(os.environ.get("HIMO_NN_CELL", "0"))
 
 
 def _chk(t, name, dtype, cols=None):
