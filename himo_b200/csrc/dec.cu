@@ -36,9 +36,9 @@ k_dec_gather(DecGatherArgs a) {
     float4 p = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
     if (i < a.n) p = a.pt4[i];
     const int key = __float_as_int(p.w);
-    float* h = a.h32 + (size_t)i * 192;
+    float* h = a.h32 ? a.h32 + (size_t)i * 192 : nullptr;
     __nv_bfloat16* hx = a.hx_planes + (size_t)i * 288;
-    __nv_bfloat16* rhx = a.rhx_planes + (size_t)i * 288;
+    __nv_bfloat16* rhx = a.rhx_planes ? a.rhx_planes + (size_t)i * 288 : nullptr;
     // point_offsets = p - ((c * voxel_size + min) + voxel_size/2), every step rounded to fp32
     // (DynamicVoxelizer._get_point_offsets, encoder.py:506-523)
     float ox = 0.f, oy = 0.f, oz = 0.f;
@@ -75,9 +75,9 @@ k_dec_gather(DecGatherArgs a) {
           }
         }
       }
-      if (ch < 24) { *(float4*)(h + c0) = *(float4*)&v[0]; *(float4*)(h + c0 + 4) = *(float4*)&v[4]; }
+      if (h && ch < 24) { *(float4*)(h + c0) = *(float4*)&v[0]; *(float4*)(h + c0 + 4) = *(float4*)&v[4]; }
       store_split8(hx + c0, a.plane_stride, a.planes, v);
-      if (ch >= 24) store_split8(rhx + c0, a.plane_stride, a.planes, v);
+      if (rhx && ch >= 24) store_split8(rhx + c0, a.plane_stride, a.planes, v);
     }
   }
 }

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "himo_b200.h"
+
 namespace himo {
 
 struct DecGatherArgs {
@@ -34,6 +36,9 @@ int dec_update(const float* zr, const float* q, float* h32, int n_pad, __nv_bflo
                long long ps, cudaStream_t stream);
 int dec_out(const float* y, int y_stride, const float4* pt4, int n, const float* w2, const float* b2,
             float* flow, cudaStream_t stream);
+// csrc/decfused.cu: the whole ConvGRU decoder after the gather in one persistent tcgen05 kernel
+int dec_fused(const __nv_bfloat16* hx, int n, int n_pad, int num_iters, const struct ::himo_deflowpp_weights* w,
+              const float4* pt4, float* flow, cudaStream_t stream);
 int dec_compact(const float4* pt4, int n, int* pos, int* n_valid, void* scan_scratch, int64_t* valid_idx,
                 const float* flow_all, float* flow_valid, cudaStream_t stream);
 

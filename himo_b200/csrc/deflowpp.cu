@@ -45,7 +45,7 @@ static size_t net_layout(int n_max, int planes, const float* vs, const float* cr
   b.V = A.take<float>((size_t)512 * 512 * 96);
   b.embed_ws_bytes = himo_embed_workspace_bytes(3, n_max, vs, cr);
   b.embed_ws = A.take<char>(b.embed_ws_bytes);
-  const size_t n_pad = (size_t)ceil_div(n_max > 0 ? n_max : 1, 128) * 128;
+  const size_t n_pad = (size_t)ceil_div(n_max > 0 ? n_max : 1, 256) * 256;
   b.h32 = A.take<float>(n_pad * 192);
   b.hx = A.take<__nv_bfloat16>((size_t)planes * n_pad * 288);
   b.rhx = A.take<__nv_bfloat16>((size_t)planes * n_pad * 288);
@@ -86,9 +86,14 @@ static int gru_gemm(const Act& in, const void* w, const float* bias, int cout, i
 
 #define HIMO_RET(expr) do { int _s = (expr); if (_s != HIMO_OK) return _s; } while (0)
 
+static int g_dec_fused = 1;
+
 }  // namespace himo
 
 using namespace himo;
+
+// A/B knob: 0 runs the ConvGRU decoder as separate GEMM + element-wise launches (the pre-fusion path).
+extern "C" int himo_deflowpp_set_fused_decoder(int enable) { g_dec_fused = enable ? 1 : 0; return HIMO_OK; }
 
 extern "C" size_t himo_deflowpp_workspace_bytes(int n_max, int planes) {
   if (n_max < 0 || (planes != 1 && planes != 2)) return 0;
@@ -167,7 +172,8 @@ extern "C" int himo_deflowpp_forward(const himo_deflowpp_weights* w, const himo_
   if (n0 > 0) {
     himo_embed_view ev;
     HIMO_RET(himo_embed_views(3, io->n_max, vs, cr, nb.embed_ws, &ev));
-    const int n_pad = ceil_div(n0, 128) * 128;
+    const bool fused = g_dec_fused && P == 2;
+    const int n_pad = fused ? ceil_div(n0, 256) * 256 : ceil_div(n0, 128) * 128;
     const long long ps = (long long)n_pad * 288;
     DecGatherArgs g;
     g.pt4 = (const float4*)ev.pt4 + (size_t)1 * io->n_max;     // frame 1 = pc0
@@ -177,8 +183,13 @@ extern "C" int himo_deflowpp_forward(const himo_deflowpp_weights* w, const himo_
     g.after = nb.V; g.c_after = 96; g.w_off = w->off_w; g.b_off = w->off_b;
     g.vx = vs[0]; g.vy = vs[1]; g.vz = vs[2]; g.x_min = cr[0]; g.y_min = cr[1]; g.z_min = cr[2];
     g.hx = vs[0] / 2; g.hy = vs[1] / 2; g.hz = vs[2] / 2; g.gx = 512;
-    g.h32 = nb.h32; g.hx_planes = nb.hx; g.rhx_planes = nb.rhx; g.planes = P; g.plane_stride = ps;
+    g.h32 = fused ? nullptr : nb.h32; g.hx_planes = nb.hx; g.rhx_planes = fused ? nullptr : nb.rhx;
+    g.planes = P; g.plane_stride = ps;
     HIMO_RET(dec_gather(g, stream));
+    if (fused) {
+      // the whole ConvGRU + head in one persistent kernel (csrc/decfused.cu)
+      HIMO_RET(dec_fused(nb.hx, n0, n_pad, io->num_iters, w, g.pt4, io->flow_all, stream));
+    } else {
     Act HX{nb.hx, n_pad / 128, 128, 288}, RHX{nb.rhx, n_pad / 128, 128, 288}, none{nullptr, 0, 0, 0};
     for (int it = 0; it < io->num_iters; ++it) {
       // The gate math could ride in the GEMM epilogue (conv.cu act 5/6, kept for reference) but measured
@@ -191,6 +202,7 @@ extern "C" int himo_deflowpp_forward(const himo_deflowpp_weights* w, const himo_
     }
     HIMO_RET(conv(HX, 0, 288, 1, w->dec0_w, w->dec0_b, 64, 1, 1, 1, none, 0, P, stream, w->dec0_s, nb.y));
     HIMO_RET(dec_out(nb.y, 64, g.pt4, n0, w->dec2_w, w->dec2_b, io->flow_all, stream));
+    }
     if (io->valid_idx && io->flow_valid && io->n_valid)
       HIMO_RET(dec_compact(g.pt4, n0, nb.pos, io->n_valid, nb.scan_scratch, io->valid_idx, io->flow_all,
                            io->flow_valid, stream));

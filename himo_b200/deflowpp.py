@@ -60,6 +60,7 @@ _lib.register("himo_deflowpp_views", c_int, [c_int, c_int, c_void_p, ctypes.POIN
 _lib.register("himo_rigid_flow", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p])
 _lib.register("himo_final_flow", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p])
 _lib.register("himo_launch_count", ctypes.c_ulonglong, [])
+_lib.register("himo_deflowpp_set_fused_decoder", c_int, [c_int])
 
 
 def cal_pose0to1(pose0: torch.Tensor, pose1: torch.Tensor) -> torch.Tensor:

@@ -256,6 +256,9 @@ typedef struct himo_deflowpp_io {
    * embedder, [2] after the backbone (UNetThreeFrame), [3] after the decoder.  NULL entries are skipped. */
   void* stage_events[4];
 } himo_deflowpp_io;
+/* A/B knob: 0 runs the ConvGRU decoder as separate GEMM + element-wise launches instead of the fused
+ * persistent kernel (default 1, split-plane mode only). */
+int himo_deflowpp_set_fused_decoder(int enable);
 typedef struct himo_deflowpp_view {
   void* canvas; void* Fstar; void* Lstar; void* Rstar; void* S; void* T; void* U; float* V;
   void* embed_ws; float* h32;

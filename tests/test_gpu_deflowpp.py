@@ -144,3 +144,24 @@ def _embed_view(net):
     res["voxel_mean"] = _read_f32(ev.voxel_mean, 3 * n * 3).reshape(3, n, 3)
     res["voxel_feats"] = _read_f32(ev.voxel_feats, 3 * n * 32).reshape(3, n, 32)
     return res
+
+
+def test_fused_decoder_matches_unfused_path():
+    """The fused persistent ConvGRU decoder (csrc/decfused.cu) against the separate GEMM + element-wise launches
+    it replaces (same weights, same frame): the two differ only in accumulation order / the 22-bit hidden state."""
+    from himo_b200 import _lib
+    L = _lib.lib()
+    sd = weights.synth_deflowpp_state_dict(3)
+    tr = frames.lidar_triple(20000, 41)
+    net = deflowpp.DeFlowPP(max_points=20480)
+    net.load_state_dict(sd)
+    batch = _batch(tr)
+    try:
+        L.himo_deflowpp_set_fused_decoder(0)
+        ref = net(batch)["flow"][0].clone()
+        L.himo_deflowpp_set_fused_decoder(1)
+        got = net(batch)["flow"][0].clone()
+    finally:
+        L.himo_deflowpp_set_fused_decoder(1)
+    assert ref.shape == got.shape and ref.abs().max() > 0
+    assert (ref - got).abs().max().item() < 2e-5
