@@ -93,6 +93,12 @@ __device__ __forceinline__ void df_store16(uint8_t* tile_hi, uint8_t* tile_lo, i
   }
 }
 
+// The gate warps rendezvous on a named barrier and ONE thread signals the leader CTA's mbarrier: a cluster-scope
+// release arrive costs a GPU-scope MEMBAR + ERRBAR (the profile showed every warp paying it per 32-channel chunk).
+__device__ __forceinline__ void df_named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __global__ void __launch_bounds__(kDfThreads, 1)
 k_dec_fused(const __grid_constant__ CUtensorMap tmHX, const __grid_constant__ CUtensorMap tmWzr,
             const __grid_constant__ CUtensorMap tmWq, const __grid_constant__ CUtensorMap tmW0,
@@ -138,10 +144,10 @@ k_dec_fused(const __grid_constant__ CUtensorMap tmHX, const __grid_constant__ CU
     umma::tma_prefetch_desc(&tmWq); umma::tma_prefetch_desc(&tmW0);
     for (int s = 0; s < 3; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
     for (int c = 0; c < 9; ++c) umma::mbar_init(&hx_tma[c], 1);
-    for (int c = 0; c < 6; ++c) umma::mbar_init(&hx_epi[c], 8);          // 4 warps x 2 CTAs
+    for (int c = 0; c < 6; ++c) umma::mbar_init(&hx_epi[c], 2);          // one aggregated arrival per CTA
     umma::mbar_init(r_full, 1); umma::mbar_init(q_full, 1); umma::mbar_init(z_full, 1); umma::mbar_init(d_full, 1);
-    for (int s = 0; s < 2; ++s) { umma::mbar_init(&rh_ready[s], 16); umma::mbar_init(&rh_empty[s], 1); }
-    umma::mbar_init(r_empty, 16); umma::mbar_init(zq_empty, 16); umma::mbar_init(d_empty, 8);
+    for (int s = 0; s < 2; ++s) { umma::mbar_init(&rh_ready[s], 2); umma::mbar_init(&rh_empty[s], 1); }
+    umma::mbar_init(r_empty, 2); umma::mbar_init(zq_empty, 2); umma::mbar_init(d_empty, 2);
     umma::mbar_init(tile_done, 1);
     umma::fence_barrier_init();
   } else if (warp == 1) {
@@ -314,12 +320,12 @@ k_dec_fused(const __grid_constant__ CUtensorMap tmHX, const __grid_constant__ CU
           umma::mbar_wait(&rh_empty[slot], ((gc >> 1) & 1) ^ 1);          // the q GEMM has read this slot's previous chunk
           df_store16(sRH + (slot * 2) * kDfTile, sRH + (slot * 2 + 1) * kDfTile, row, half * 2, v);
           umma::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) umma::mbar_arrive_cluster(slot ? a_rh_ready1 : a_rh_ready0);
+          df_named_sync(1, 256);
+          if (warp == 2 && lane == 0) umma::mbar_arrive_cluster(slot ? a_rh_ready1 : a_rh_ready0);
         }
         umma::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) umma::mbar_arrive_cluster(a_r_empty);
+        df_named_sync(1, 256);
+        if (warp == 2 && lane == 0) umma::mbar_arrive_cluster(a_r_empty);
         // ---- z = sigmoid(Z), q = tanh(Q), h <- (1-z) h + z q, written back into the operand tile
         umma::mbar_wait(z_full, (uint32_t)(n_it & 1));                     // (the commit also covers the q GEMM)
         umma::tc_fence_after();
@@ -343,13 +349,13 @@ k_dec_fused(const __grid_constant__ CUtensorMap tmHX, const __grid_constant__ CU
           df_store16(sHX + (c * 2) * kDfTile, sHX + (c * 2 + 1) * kDfTile, row, j0, hn);
           if (g & 1) {   // both 16-column groups of chunk c are written: hand it to the next GEMM
             umma::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) umma::mbar_arrive_cluster(a_hx_epi0 + 8u * (uint32_t)c);
+            df_named_sync(2 + half, 128);                          // the four warps that own this column half
+            if ((warp == 2 || warp == 6) && lane == 0) umma::mbar_arrive_cluster(a_hx_epi0 + 8u * (uint32_t)c);
           }
         }
         umma::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) umma::mbar_arrive_cluster(a_zq_empty);
+        df_named_sync(1, 256);
+        if (warp == 2 && lane == 0) umma::mbar_arrive_cluster(a_zq_empty);
       }
       // ---- head: flow = W_2 GELU(Y + b_0) + b_2 (one warp per TMEM lane quadrant)
       if (half == 0) {
@@ -374,8 +380,8 @@ k_dec_fused(const __grid_constant__ CUtensorMap tmHX, const __grid_constant__ CU
           p.flow[3 * gi] = valid ? o0 : 0.f; p.flow[3 * gi + 1] = valid ? o1 : 0.f; p.flow[3 * gi + 2] = valid ? o2 : 0.f;
         }
         umma::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) umma::mbar_arrive_cluster(a_d_empty);
+        df_named_sync(2, 128);
+        if (warp == 2 && lane == 0) umma::mbar_arrive_cluster(a_d_empty);
       }
     }
   }

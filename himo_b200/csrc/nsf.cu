@@ -176,6 +176,7 @@ struct NsfBufs {
   float* head_part;                // [head_blocks][kHeadPart]
   float* gW0;                      // [128][3] + [128] bias
   float* gb;                       // [7][128] bias grads of layers 1..7 (scaled)
+  float* rs_part;                  // [kRowSplit][4][128] row-sum partials
   NsfCtl* ctl;
   float grad_scale;                // power of two S; every backward tensor carries S/N instead of 1/N
 };
@@ -192,24 +193,64 @@ __host__ __device__ inline int nsf_off_b(int l) {
 }
 constexpr int kNsfParams = 128 * 3 + 128 + 7 * (128 * 128 + 128) + 3 * 128 + 3;   // 116483
 
-// layer 0: h1 = relu(W0 x + b0), K = 3 -> plain FMAs; writes row-major and transposed planes
+// layer 0: h1 = relu(W0 x + b0), K = 3 -> plain FMAs; writes row-major and transposed planes.
+// One block = 64 points x 128 features.  Phase A: a thread owns 32 consecutive features of one point (64-byte
+// row-major stores per plane) and parks the 16-bit planes in shared memory; phase B: a thread owns 32 consecutive
+// points of one feature and writes the transposed planes with 16-byte stores (the element-wise version issued
+// 2-byte stores n_pad elements apart: 235 us per iteration at 100 k points).
+constexpr int kL0Pts = 64;
 __global__ void __launch_bounds__(256)
 k_nsf_l0_fwd(NsfBufs b) {
   if (b.ctl->stop) return;
+  __shared__ __align__(16) unsigned short s_pl[2][128][kL0Pts + 8];
   const float* W = b.params + nsf_off_w(0);
   const float* bias = b.params + nsf_off_b(0);
-  const long long total = (long long)b.n_pad * 128;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(t % 128);
-    const long long i = t / 128;
-    const float4 p = b.x4[i];
-    float v = __ldg(W + j * 3) * p.x;
-    v = fmaf(__ldg(W + j * 3 + 1), p.y, v);
-    v = fmaf(__ldg(W + j * 3 + 2), p.z, v);
-    v = fmaxf(v + __ldg(bias + j), 0.f);
-    umma::store_split(b.H[1] + i * 128 + j, b.ps, b.planes, v);
-    umma::store_split(b.HT[1] + (long long)j * b.n_pad + i, b.ps, b.planes, v);
+  const bool split = b.planes == 2;
+  for (long long base = (long long)blockIdx.x * kL0Pts; base < b.n_pad; base += (long long)gridDim.x * kL0Pts) {
+    {
+      const int pi = threadIdx.x >> 2, j0 = (threadIdx.x & 3) * 32;
+      const long long i = base + pi;
+      const float4 p = b.x4[i];
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float v[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = j0 + 2 * k + u;
+          float t = __ldg(W + j * 3) * p.x;
+          t = fmaf(__ldg(W + j * 3 + 1), p.y, t);
+          t = fmaf(__ldg(W + j * 3 + 2), p.z, t);
+          v[u] = fmaxf(t + __ldg(bias + j), 0.f);
+        }
+        umma::pack_split2(v[0], v[1], split, hi[k], lo[k]);
+        s_pl[0][j0 + 2 * k][pi] = (unsigned short)(hi[k] & 0xffffu);
+        s_pl[0][j0 + 2 * k + 1][pi] = (unsigned short)(hi[k] >> 16);
+        if (split) {
+          s_pl[1][j0 + 2 * k][pi] = (unsigned short)(lo[k] & 0xffffu);
+          s_pl[1][j0 + 2 * k + 1][pi] = (unsigned short)(lo[k] >> 16);
+        }
+      }
+      uint4* d0 = (uint4*)(b.H[1] + i * 128 + j0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d0[k] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+      if (split) {
+        uint4* d1 = (uint4*)(b.H[1] + b.ps + i * 128 + j0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d1[k] = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
+      }
+    }
+    __syncthreads();
+    {
+      const int f = threadIdx.x >> 1, p0 = (threadIdx.x & 1) * 32;
+      for (int pl = 0; pl < b.planes; ++pl) {
+        const uint4* src = (const uint4*)&s_pl[pl][f][p0];
+        uint4* dst = (uint4*)(b.HT[1] + (long long)pl * b.ps + (long long)f * b.n_pad + base + p0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[k] = src[k];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -285,31 +326,45 @@ k_nsf_head(NsfBufs b, const float* __restrict__ D, NsfVol vol) {
   // backward through the output layer + ReLU mask of h8
   float* part = b.head_part + (size_t)blockIdx.x * kHeadPart;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int j = 0; j < 128; ++j) {
-    const float h = i < b.n_pad ? load_split(hT + (long long)j * b.n_pad + (i < b.n_pad ? i : 0), b.ps, b.planes) : 0.f;
-    float dh = fmaf(d2, __ldg(W8 + 256 + j), fmaf(d1, __ldg(W8 + 128 + j), d0 * __ldg(W8 + j)));
-    if (!(h > 0.f)) dh = 0.f;
-    if (i < b.n_pad) {
-      umma::store_split(b.DL[0] + (long long)i * 128 + j, b.ps, b.planes, dh);
-      umma::store_split(b.DLT[0] + (long long)j * b.n_pad + i, b.ps, b.planes, dh);
-    }
-    // dW8[k][j] partial = sum over the block's points of d_k * h_j (fixed shuffle tree => deterministic)
-    float a0 = d0 * h, a1 = d1 * h, a2 = d2 * h;
+  __shared__ float red_w[kHeadThreads / 32][3][128];
+  const bool in_pad = i < b.n_pad;
+  const bool split = b.planes == 2;
+  for (int j0 = 0; j0 < 128; j0 += 8) {
+    uint32_t hi[4], lo[4];
+    float dhv[8];
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, s);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, s);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, s);
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u;
+      const float h = in_pad ? load_split(hT + (long long)j * b.n_pad + i, b.ps, b.planes) : 0.f;
+      float dh = fmaf(d2, __ldg(W8 + 256 + j), fmaf(d1, __ldg(W8 + 128 + j), d0 * __ldg(W8 + j)));
+      if (!(h > 0.f)) dh = 0.f;
+      dhv[u] = dh;
+      if (in_pad) umma::store_split(b.DLT[0] + (long long)j * b.n_pad + i, b.ps, b.planes, dh);   // lanes = consecutive points
+      // dW8[k][j] partial = sum over the block's points of d_k * h_j (fixed shuffle tree => deterministic)
+      float a0 = d0 * h, a1 = d1 * h, a2 = d2 * h;
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, sft);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, sft);
+      }
+      if (lane == 0) { red_w[warp][0][j] = a0; red_w[warp][1][j] = a1; red_w[warp][2][j] = a2; }
     }
-    if (lane == 0) { red[warp][0] = a0; red[warp][1] = a1; red[warp][2] = a2; }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-      float s = 0.f;
-      for (int wv = 0; wv < kHeadThreads / 32; ++wv) s += red[wv][threadIdx.x];
-      part[threadIdx.x * 128 + j] = s;
+    if (in_pad) {   // row-major copy: 8 features = one 16-byte store per plane
+#pragma unroll
+      for (int u = 0; u < 4; ++u) umma::pack_split2(dhv[2 * u], dhv[2 * u + 1], split, hi[u], lo[u]);
+      *(uint4*)(b.DL[0] + (long long)i * 128 + j0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (split) *(uint4*)(b.DL[0] + b.ps + (long long)i * 128 + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-    __syncthreads();
   }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 384; t += kHeadThreads) {
+    const int k = t >> 7, j = t & 127;
+    float sacc = 0.f;
+    for (int wv = 0; wv < kHeadThreads / 32; ++wv) sacc += red_w[wv][k][j];
+    part[k * 128 + j] = sacc;
+  }
+  __syncthreads();
   float a0 = d0, a1 = d1, a2 = d2, a3 = val;
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
@@ -329,11 +384,16 @@ k_nsf_head(NsfBufs b, const float* __restrict__ D, NsfVol vol) {
 
 // loss reduction + best-flow bookkeeping + EarlyStopping.step (nsfp_module.py:65-82), single thread.
 __global__ void k_nsf_control(NsfBufs b, int head_blocks, float min_delta, int patience) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
   NsfCtl* c = b.ctl;
-  if (c->stop) { c->snapshot = 0; return; }
+  const int stopped = c->stop;
   double s = 0.0;
-  for (int k = 0; k < head_blocks; ++k) s += (double)b.head_part[(size_t)k * kHeadPart + 387];
+  if (!stopped)   // 32 strided partial sums + a fixed shuffle tree (deterministic)
+    for (int k = threadIdx.x; k < head_blocks; k += 32) s += (double)b.head_part[(size_t)k * kHeadPart + 387];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (threadIdx.x != 0) return;
+  if (stopped) { c->snapshot = 0; return; }
   const float loss = (float)(s / (double)b.n);
   c->loss = loss;
   c->iters += 1;
@@ -358,17 +418,43 @@ k_nsf_snapshot(NsfBufs b) {
 }
 
 // bias gradient of layer l (1..7) = row sums of delta_{l+1}^T; for layer 0 also dW0 = delta_1^T x.
-// One block per feature, fixed-order tree => deterministic.
-__global__ void __launch_bounds__(256)
-k_nsf_rowsum(NsfBufs b, const __nv_bfloat16* __restrict__ dT, float* __restrict__ out_b, float* __restrict__ out_w0) {
+// grid (128 features, kRowSplit point ranges): 16-byte loads of 8 consecutive points per plane, fixed-order
+// reductions (deterministic); k_nsf_rowsum_final adds the kRowSplit partials in index order.  (The one-block-per-
+// feature version with 2-byte loads took 210 us per layer = 48 % of an iteration.)
+constexpr int kRowSplit = 16;
+__global__ void __launch_bounds__(128)
+k_nsf_rowsum(NsfBufs b, const __nv_bfloat16* __restrict__ dT, float* __restrict__ part, int with_w0) {
   if (b.ctl->stop) return;
-  __shared__ float red[8][4];
-  const int f = blockIdx.x;
+  __shared__ float red[4][4];
+  const int f = blockIdx.x, sp = blockIdx.y;
+  const int nvec = b.n_pad >> 3;
+  const int per = (nvec + kRowSplit - 1) / kRowSplit;
+  const int v0 = sp * per, v1 = min(v0 + per, nvec);
+  const uint4* hi = (const uint4*)(dT + (long long)f * b.n_pad);
+  const uint4* lo = (const uint4*)(dT + b.ps + (long long)f * b.n_pad);
   float s = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
-  for (int i = threadIdx.x; i < b.n; i += blockDim.x) {
-    const float v = load_split(dT + (long long)f * b.n_pad + i, b.ps, b.planes);
-    s += v;
-    if (out_w0) { const float4 p = b.x4[i]; sx = fmaf(v, p.x, sx); sy = fmaf(v, p.y, sy); sz = fmaf(v, p.z, sz); }
+  for (int v = v0 + threadIdx.x; v < v1; v += 128) {
+    const uint4 a = hi[v];
+    const uint32_t aa[4] = {a.x, a.y, a.z, a.w};
+    float val[8];
+    if (b.planes == 2) {
+      const uint4 l = lo[v];
+      const uint32_t ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&aa[k]));
+        const float2 l2 = __half22float2(*reinterpret_cast<const __half2*>(&ll[k]));
+        val[2 * k] = h2.x + l2.x; val[2 * k + 1] = h2.y + l2.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { val[2 * k] = __uint_as_float(aa[k] << 16); val[2 * k + 1] = __uint_as_float(aa[k] & 0xffff0000u); }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s += val[k];
+      if (with_w0) { const float4 p = b.x4[(size_t)v * 8 + k]; sx = fmaf(val[k], p.x, sx); sy = fmaf(val[k], p.y, sy); sz = fmaf(val[k], p.z, sz); }
+    }
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -380,12 +466,22 @@ k_nsf_rowsum(NsfBufs b, const __nv_bfloat16* __restrict__ dT, float* __restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) { red[warp][0] = s; red[warp][1] = sx; red[warp][2] = sy; red[warp][3] = sz; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int wv = 0; wv < 8; ++wv) for (int k = 0; k < 4; ++k) t[k] += red[wv][k];
-    out_b[f] = t[0];
-    if (out_w0) { out_w0[f * 3] = t[1]; out_w0[f * 3 + 1] = t[2]; out_w0[f * 3 + 2] = t[3]; }
+  if (threadIdx.x < 4) {
+    float t = 0.f;
+    for (int wv = 0; wv < 4; ++wv) t += red[wv][threadIdx.x];
+    part[((size_t)sp * 4 + threadIdx.x) * 128 + f] = t;
   }
+}
+__global__ void __launch_bounds__(128)
+k_nsf_rowsum_final(NsfBufs b, const float* __restrict__ part, float* __restrict__ out_b, float* __restrict__ out_w0) {
+  if (b.ctl->stop) return;
+  const int f = threadIdx.x;
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int sp = 0; sp < kRowSplit; ++sp)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] += part[((size_t)sp * 4 + k) * 128 + f];
+  out_b[f] = t[0];
+  if (out_w0) { out_w0[f * 3] = t[1]; out_w0[f * 3 + 1] = t[2]; out_w0[f * 3 + 2] = t[3]; }
 }
 
 struct NsfAdamArgs {
@@ -499,6 +595,7 @@ static size_t nsf_layout(int n_max, int planes, NsfLayout* L, void* base) {
   l.b.head_part = A.take<float>((size_t)l.head_blocks * kHeadPart);
   l.b.gW0 = A.take<float>(128 * 3 + 128);
   l.b.gb = A.take<float>(7 * 128);
+  l.b.rs_part = A.take<float>(16 * 4 * 128);
   l.b.ctl = A.take<NsfCtl>(1);
   l.k_split = 32 * ceil_div(n_pad, 32 * kNumSMs);
   l.splits = ceil_div(n_pad, l.k_split);
@@ -617,7 +714,7 @@ extern "C" int himo_nsf_optimize(const himo_nsf_desc* d, void* stream_) {
 
   const float wscale = P == 2 ? 1.0f / kNsfWScale : 1.0f;
   auto iteration = [&]() -> int {
-    k_nsf_l0_fwd<<<kNumSMs * 8, 256, 0, stream>>>(b); HIMO_LAUNCH_RET();
+    k_nsf_l0_fwd<<<min(n_pad / kL0Pts, kNumSMs * 8), 256, 0, stream>>>(b); HIMO_LAUNCH_RET();
     for (int l = 1; l < kNsfLayers; ++l) {                      // h_{l+1} = relu(W_l h_l + b_l)
       himo_conv_desc g = {};
       g.in = b.H[l]; g.in_planes = P; g.in_plane_stride = b.ps; g.H_in = n_pad / 128; g.W_in = 128;
@@ -640,7 +737,8 @@ extern "C" int himo_nsf_optimize(const himo_nsf_desc* d, void* stream_) {
       g.n_groups = splits; g.cin_group_stride = k_split; g.cout_group_stride = 0; g.acc_scale = 1.f;
       g.b_group_k_stride = k_split; g.out_group_pix_stride = 128; g.b_k_total = n_pad; g.stop_flag = &b.ctl->stop;
       HIMO_RET(nsf_gemm(g, stream));
-      k_nsf_rowsum<<<128, 256, 0, stream>>>(b, b.DLT[cur], b.gb + (l - 1) * 128, nullptr); HIMO_LAUNCH_RET();
+      k_nsf_rowsum<<<dim3(128, kRowSplit), 128, 0, stream>>>(b, b.DLT[cur], b.rs_part, 0); HIMO_LAUNCH_RET();
+      k_nsf_rowsum_final<<<1, 128, 0, stream>>>(b, b.rs_part, b.gb + (l - 1) * 128, nullptr); HIMO_LAUNCH_RET();
       // delta_l = (delta_{l+1} W_l) * relu'(h_l)
       himo_conv_desc q = {};
       q.in = b.DL[cur]; q.in_planes = P; q.in_plane_stride = b.ps; q.H_in = n_pad / 128; q.W_in = 128;
@@ -651,7 +749,8 @@ extern "C" int himo_nsf_optimize(const himo_nsf_desc* d, void* stream_) {
       HIMO_RET(nsf_gemm(q, stream));
       cur ^= 1;
     }
-    k_nsf_rowsum<<<128, 256, 0, stream>>>(b, b.DLT[cur], b.gW0 + 384, b.gW0); HIMO_LAUNCH_RET();
+    k_nsf_rowsum<<<dim3(128, kRowSplit), 128, 0, stream>>>(b, b.DLT[cur], b.rs_part, 1); HIMO_LAUNCH_RET();
+    k_nsf_rowsum_final<<<1, 128, 0, stream>>>(b, b.rs_part, b.gW0 + 384, b.gW0); HIMO_LAUNCH_RET();
     k_nsf_adam<<<kNumSMs * 2, 256, 0, stream>>>(ad); HIMO_LAUNCH_RET();
     return HIMO_OK;
   };
