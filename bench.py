@@ -75,7 +75,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -84,10 +84,19 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: brackets the timed region inside an already running sampler."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
+        window = self.rows[first:last] if last is not None else self.rows[first:]
+        if len(window) < 2:          # very short timed region: widen to the neighbouring samples (still under load)
+            window = self.rows[max(0, first - 2):(last + 2 if last is not None else None)]
+        self.rows = window
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -152,7 +161,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
@@ -225,11 +234,18 @@ def main():
         return ms
 
     # ---- warm-up, then the timed kernel-only region
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # started before the warm-up so that it is already streaming samples
     for i in range(args.warmup):
         step_resident(i)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    for _ in range(200):                 # nvidia-smi takes a moment to produce its first row
+        if sampler.mark() > 0:
+            break
+        step_resident(0)
+        torch.cuda.synchronize()
+        time.sleep(0.01)
+    mark0 = sampler.mark()
     launches0 = L.himo_launch_count()
     ms_total = timed(step_resident, args.steps)
     launches = (L.himo_launch_count() - launches0)
@@ -258,7 +274,7 @@ def main():
         ms_e2e = float(t.item())
     barrier()
     e2e_value = world * args.steps / (ms_e2e / 1e3)
-    clocks = sampler.stop()
+    clocks = sampler.stop(mark0, sampler.mark())
     h2d, d2h = eng.h2d_bytes, eng.d2h_bytes
 
     # ---- per-stage split (one profiled pass per frame; CUDA events on the launching stream)
@@ -288,6 +304,12 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "B200_PROFILING.md fallback"
     fl = backbone_flops()
     achieved = fl / (stage[1] / 1e3) / 1e12
+    traffic = None        # dram__bytes_read.sum + dram__bytes_write.sum of the conv launches of one step (ncu capture)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_backbone_traffic.json")))
+        traffic = float(tj["dram_bytes_read_per_step"]) + float(tj["dram_bytes_write_per_step"])
+    except (OSError, KeyError, ValueError):
+        pass
     mma_mult = 3 if args.precision == "fp32" else 1
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -302,9 +324,12 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "stages_ms": {"embedder": stage[0], "backbone": stage[1], "decoder": stage[2]},
-        "roofline": {"bound": "tensor", "kernel": "k_conv_umma (all 32 backbone launches of a step)",
+        "roofline": {"bound": "tensor", "kernel": "k_conv_umma (the 29 convolution launches of a step; the stage time "
+                                                   "also holds the 3 bilinear upsamples, 3 % of it)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_unit": "DRAM bytes per step over those launches (ncu, profiles/"
+                                                         "r01_backbone_traffic.json); algorithmic = FLOPs, see DESIGN.md",
+                     "peak_source": peak_src,
                      "algorithmic_gflop_per_step": fl / 1e9, "tensor_issue_multiplier": mma_mult,
                      "tensor_issue_frac": achieved * mma_mult / peak_tf},
     }

@@ -105,12 +105,12 @@ k_nsf_occupancy(const float* __restrict__ pc1, int n, NsfVol v, float* __restric
 
 // One raster pass of the FastGeodis Euclidean transform advances along `axis`; plane p takes
 //   new[p] = min(old[p], min over the 3x3 neighbourhood of new[p -/+ 1] + step length).
-// A block owns a 32x32 tile of the plane and advances kDtSteps planes per launch from a halo of kDtSteps
+// A block owns a kDtTile x kDtTile tile of the plane and advances kDtSteps planes per launch from a halo of kDtSteps
 // cells (the dependency cone widens by one cell per plane), so a pass costs n_axis/kDtSteps launches
 // instead of n_axis.  Halo cells may read a neighbour block's already-updated value of plane p; because
 // the update is an idempotent min over the same inputs this cannot change the result.
-constexpr int kDtSteps = 8;
-constexpr int kDtTile = 32;
+constexpr int kDtSteps = 16;
+constexpr int kDtTile = 16;   // small tiles: the axis-0/1 planes are only ~50 k cells, 32x32 tiles left most SMs idle
 constexpr int kDtReg = kDtTile + 2 * kDtSteps;   // 48
 
 __global__ void __launch_bounds__(256)
@@ -120,7 +120,9 @@ k_nsf_dt_pass(float* __restrict__ d, int n0, int n1, int n2, int axis, int dir, 
   __shared__ float buf[2][kDtReg][kDtReg + 1];
   const int n[3] = {n0, n1, n2};
   const long long st[3] = {(long long)n1 * n2, (long long)n2, 1};
-  const int a = axis, h = (axis + 1) % 3, w = (axis + 2) % 3;
+  // in-plane axes: w (the fast thread index) is always the higher-numbered axis = the smaller memory stride, so
+  // that a warp reads consecutive addresses (with (axis+1)%3, (axis+2)%3 the axis-1 passes strode n1*n2 floats)
+  const int a = axis, h = axis == 0 ? 1 : 0, w = axis == 2 ? 1 : 2;
   const int h0 = blockIdx.y * kDtTile - kDtSteps, w0 = blockIdx.x * kDtTile - kDtSteps;
   const int pp = p_begin - dir;     // plane already final
   for (int t = threadIdx.x; t < kDtReg * kDtReg; t += blockDim.x) {
@@ -657,7 +659,7 @@ extern "C" int himo_nsf_dt_build(const float* pc1, int n1, const float* lo, cons
   const float l00 = sqrtf(sp * sp), l01 = sqrtf(sp * sp + sp * sp), l11 = sqrtf(sp * sp + sp * sp + sp * sp);
   const int n[3] = {dims[0], dims[1], dims[2]};
   for (int axis = 0; axis < 3; ++axis) {
-    const int h = (axis + 1) % 3, w = (axis + 2) % 3;
+    const int h = axis == 0 ? 1 : 0, w = axis == 2 ? 1 : 2;
     dim3 grid(ceil_div(n[w], kDtTile), ceil_div(n[h], kDtTile));
     for (int dir = 1; dir >= -1; dir -= 2) {
       int p = dir > 0 ? 1 : n[axis] - 2;
