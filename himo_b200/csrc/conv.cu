@@ -88,22 +88,29 @@ __device__ __forceinline__ float gelu_erf(float v) {
 // CG == 2: a pair of CTAs (thread-block cluster of 2) computes a 256-pixel x BN tile with
 // tcgen05.mma.cta_group::2: each CTA stages its own 128 pixels of A and only HALF of the weight rows, the
 // leader CTA issues the MMAs for both, and every weight byte is fetched from L2 once per 256 pixels.
-template <int BN, int P, int NX, int CG>
+// WR > 0 ("weights resident"): the layer's whole weight tensor -- WR = taps * k_chunks tiles of BN rows x 32
+// channels per plane -- is loaded into shared memory ONCE per CTA and every pipeline stage carries only the
+// activation tile.  For the 64-channel encoder layers the weights (74 / 147 KB) were re-fetched from L2 for every
+// 128-pixel tile and out-weighed the activation traffic 3:2.
+template <int BN, int P, int NX, int CG, int WR = 0>
 struct ConvCfg {
   static constexpr int kARows = NX == 3 ? 136 : 128;                 // smem rows reserved per A plane
   static constexpr int kARowsTx = NX == 3 ? 130 : 128;               // rows TMA really writes
   static constexpr int kABytes = kARows * kConvRowB;
   static constexpr int kBRows = BN / CG;                             // weight rows staged by this CTA
   static constexpr int kBBytes = kBRows * kConvRowB;
-  static constexpr int kStageBytes = P * kABytes + NX * P * kBBytes;
-  static constexpr int kTxBytes = P * kARowsTx * kConvRowB + NX * P * kBBytes;
-  static constexpr int kStagesRaw = (220 * 1024) / kStageBytes;
+  static constexpr int kBResBytes = WR * P * kBBytes;
+  static constexpr int kStageBytes = WR ? P * kABytes : P * kABytes + NX * P * kBBytes;
+  static constexpr int kTxBytes = WR ? P * kARowsTx * kConvRowB : P * kARowsTx * kConvRowB + NX * P * kBBytes;
+  static constexpr int kStagesRaw = (220 * 1024 - kBResBytes) / kStageBytes;
   static constexpr int STAGES = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kBResOffset = STAGES * kStageBytes;          // (TMA and tcgen05 both swizzle on absolute address bits)
+  static constexpr int kBarOffset = kBResOffset + kBResBytes;
+  static_assert(WR == 0 || CG == 1, "resident weights are implemented for single-CTA tiles");
   static constexpr int kBiasOffset = kBarOffset + 512;               // fp32 bias vector staged once per CTA
   static constexpr int kMaxBias = 1024;
   static constexpr int kTotal = kBiasOffset + kMaxBias * 4 + 128;   // barriers + bias + alignment slack
-  static constexpr int kUsedCols = P == 2 ? 3 * BN : 2 * BN;
+  static constexpr int kUsedCols = P == 2 ? 4 * BN : 2 * BN;         // split mode: 2 main + 2 cross accumulators
   static constexpr int kTmemCols = kUsedCols <= 64 ? 64 : kUsedCols <= 128 ? 128 : kUsedCols <= 256 ? 256 : 512;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
@@ -309,14 +316,16 @@ __device__ __forceinline__ void conv_epilogue_fast(const float* acc, const ConvP
 //   * the hi*hi chain is cut every `flush_stages` stages: the MMA warp ping-pongs between two "main"
 //     accumulators and the epilogue warps drain the finished one into fp32 registers (round-to-nearest)
 //     while the tensor core fills the other.
-// TMEM columns: main0 [0,BN), main1 [BN,2BN), cross [2BN,3BN).
+// TMEM columns: main0 [0,BN), main1 [BN,2BN), cross0 [2BN,3BN), cross1 [3BN,4BN): the cross accumulator is
+// double-buffered by tile parity so that the MMAs of tile i+1 never wait for the drain of tile i (with short-K
+// tiles -- 6 stages for the 64-channel layers, 4 for the FastNSF GEMMs -- that bubble was ~20 % of a tile).
 // The kernel is persistent: one CTA per SM walks the tile list, barrier phases run across tiles, and the
 // store epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int P, int NX, int CG>
+template <int BN, int P, int NX, int CG, int WR = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const ConvParams p) {
-  using C = ConvCfg<BN, P, NX, CG>;
+  using C = ConvCfg<BN, P, NX, CG, WR>;
   constexpr int STAGES = C::STAGES;
   constexpr int kHalf = BN / 2;            // columns owned by one epilogue thread
   constexpr int kGroups = kHalf / 16;
@@ -328,8 +337,9 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full_bar = empty_bar + STAGES;     // [2]
   uint64_t* acc_empty_bar = acc_full_bar + 2;      // [2]
-  uint64_t* cross_empty_bar = acc_empty_bar + 2;   // [1]
-  uint32_t* tmem_ptr_smem = (uint32_t*)(cross_empty_bar + 1);
+  uint64_t* cross_empty_bar = acc_empty_bar + 2;   // [2]
+  uint64_t* bres_bar = cross_empty_bar + 2;       // [1] resident weights landed (WR mode)
+  uint32_t* tmem_ptr_smem = (uint32_t*)(bres_bar + 1);
   float* bias_smem = (float*)(smem + C::kBiasOffset);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -354,7 +364,9 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       umma::mbar_init(&acc_full_bar[b], 1);
       umma::mbar_init(&acc_empty_bar[b], kConvEpiWarps * CG);    // CG == 2: both CTAs' epilogues report to the leader
     }
-    umma::mbar_init(cross_empty_bar, kConvEpiWarps * CG);
+    umma::mbar_init(&cross_empty_bar[0], kConvEpiWarps * CG);
+    umma::mbar_init(&cross_empty_bar[1], kConvEpiWarps * CG);
+    umma::mbar_init(bres_bar, 1);
     umma::fence_barrier_init();
   } else if (warp == 1) {
     if (CG == 2) umma::tmem_alloc_2cta(tmem_ptr_smem, C::kTmemCols);
@@ -383,6 +395,19 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     {
       // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
       uint32_t git = 0;
+      if (WR > 0) {   // the whole weight tensor, once (all groups and tiles of this layer share it: one N tile)
+        if (umma::elect_one()) {
+          umma::mbar_arrive_expect_tx(bres_bar, (uint32_t)C::kBResBytes);
+          for (int t = 0; t < WR; ++t) {
+            const int tap = t / p.k_chunks, kc = t - tap * p.k_chunks;
+#pragma unroll
+            for (int pl = 0; pl < P; ++pl)
+              umma::tma_load_3d(smem + C::kBResOffset + (t * P + pl) * C::kBBytes, &tmB, bres_bar,
+                                tap * p.Cin + kc * kConvBK, 0, pl);
+          }
+        }
+        __syncwarp();
+      }
       for (int tile = worker; tile < total_work; tile += n_workers) {
         int g, x0, y0, n0;
         decode(tile, g, x0, y0, n0);
@@ -407,7 +432,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               else umma::tma_load_4d(a_dst + pl * C::kABytes, &tmA, &full_bar[s], cin0 + kc * kConvBK, x0 - 1, y0 + ky - 1, pl);
             }
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
+            for (int kx = 0; kx < (WR ? 0 : 3); ++kx)
 #pragma unroll
               for (int pl = 0; pl < P; ++pl) {
                 const int kk = bk0 + (ky * 3 + kx) * p.Cin + kc * kConvBK;
@@ -425,7 +450,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                      x0 * p.stride + kx - p.pad, y0 * p.stride + ky - p.pad, pl);
             }
 #pragma unroll
-            for (int pl = 0; pl < P; ++pl) {
+            for (int pl = 0; pl < (WR ? 0 : P); ++pl) {
               const int kk = bk0 + tap * p.Cin + kc * kConvBK;
               if (CG == 2) umma::tma_load_3d_2cta(b_dst + pl * C::kBBytes, &tmB, fb, kk, nb0, pl);
               else umma::tma_load_3d(b_dst + pl * C::kBBytes, &tmB, &full_bar[s], kk, nb0, pl);
@@ -441,7 +466,6 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // kind::f16 format codes: 0 = fp16 (split mode, both planes), 1 = bf16 (single-plane mode)
       constexpr uint32_t kFmt = P == 2 ? 0u : 1u;
       constexpr uint32_t idesc = umma::idesc_f16kind_f32(kConvBM * CG, BN, kFmt, kFmt);
-      const uint32_t tmem_cross = tmem_base + 2 * BN;
       auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
         if (CG == 2) umma::mma_bf16_ss_2cta(d, a, b, id, acc);
         else umma::mma_bf16_ss(d, a, b, id, acc);
@@ -451,9 +475,12 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         else umma::mma_commit(bar);
       };
       uint32_t git = 0, gch = 0, tcount = 0;
+      if (WR > 0) { umma::mbar_wait(bres_bar, 0); umma::tc_fence_after(); }
+      const uint32_t bres_addr = umma::smem_u32(smem + C::kBResOffset);
       for (int tile = worker; tile < total_work; tile += n_workers, ++tcount) {
-        if (P == 2) {   // the epilogue must have read the previous tile's cross accumulator
-          umma::mbar_wait(cross_empty_bar, (tcount & 1) ^ 1);
+        const uint32_t tmem_cross = tmem_base + (2 + (tcount & 1)) * BN;
+        if (P == 2) {   // the epilogue must have read this cross accumulator's previous tile (two tiles ago)
+          umma::mbar_wait(&cross_empty_bar[tcount & 1], ((tcount >> 1) & 1) ^ 1);
           umma::tc_fence_after();
         }
         int it = 0;
@@ -469,15 +496,22 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             umma::mbar_wait(&full_bar[s], ph);
             umma::tc_fence_after();
             const uint32_t a_addr = umma::smem_u32(smem + s * C::kStageBytes);
-            const uint32_t b_addr = a_addr + P * C::kABytes;
+            uint32_t b_addr = a_addr + P * C::kABytes;
+            if (WR > 0) {   // resident tile index t = tap * k_chunks + kc; the kx taps of a haloed stage are k_chunks apart
+              int t0;
+              if (NX == 3) { const int kc = it / 3, ky = it - kc * 3; t0 = ky * 3 * p.k_chunks + kc; }
+              else t0 = it;                                  // it = tap * k_chunks + kc already
+              b_addr = bres_addr + (uint32_t)(t0 * P * C::kBBytes);
+            }
+            const uint32_t b_tap_stride = WR > 0 ? (uint32_t)(p.k_chunks * P * C::kBBytes) : (uint32_t)(P * C::kBBytes);
             if (umma::elect_one()) {
 #pragma unroll
             for (int kx = 0; kx < NX; ++kx) {
               // halo mode: tap kx reads rows [kx, kx+128) of the haloed A tile
               const uint64_t a_hi = umma::smem_desc_kmajor<kConvRowB>(a_addr + kx * kConvRowB);
               const uint64_t a_lo = umma::smem_desc_kmajor<kConvRowB>(a_addr + (P - 1) * C::kABytes + kx * kConvRowB);
-              const uint64_t b_hi = umma::smem_desc_kmajor<kConvRowB>(b_addr + (kx * P) * C::kBBytes);
-              const uint64_t b_lo = umma::smem_desc_kmajor<kConvRowB>(b_addr + (kx * P + P - 1) * C::kBBytes);
+              const uint64_t b_hi = umma::smem_desc_kmajor<kConvRowB>(b_addr + kx * b_tap_stride);
+              const uint64_t b_lo = umma::smem_desc_kmajor<kConvRowB>(b_addr + kx * b_tap_stride + (P - 1) * C::kBBytes);
 #pragma unroll
               for (int k = 0; k < kConvBK / 16; ++k) {
                 const uint64_t koff = (uint64_t)(k * 32 >> 4);  // 16 elements = 32 bytes along K
@@ -507,8 +541,10 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // CG == 2: "accumulator drained" is reported to the leader CTA, whose MMA warp owns the schedule
     const uint32_t ae0 = CG == 2 ? umma::mapa_u32(umma::smem_u32(&acc_empty_bar[0]), 0) : 0u;
     const uint32_t ae1 = CG == 2 ? umma::mapa_u32(umma::smem_u32(&acc_empty_bar[1]), 0) : 0u;
-    const uint32_t ce = CG == 2 ? umma::mapa_u32(umma::smem_u32(cross_empty_bar), 0) : 0u;
-    for (int tile = worker; tile < total_work; tile += n_workers) {
+    const uint32_t ce0 = CG == 2 ? umma::mapa_u32(umma::smem_u32(&cross_empty_bar[0]), 0) : 0u;
+    const uint32_t ce1 = CG == 2 ? umma::mapa_u32(umma::smem_u32(&cross_empty_bar[1]), 0) : 0u;
+    uint32_t tcount = 0;
+    for (int tile = worker; tile < total_work; tile += n_workers, ++tcount) {
       int g, x0, y0, n0;
       decode(tile, g, x0, y0, n0);
       float acc[kHalf];
@@ -534,16 +570,16 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         };
         drain((uint32_t)(buf * BN));
-        if (P == 2 && chunk == n_chunks - 1) drain((uint32_t)(2 * BN));   // the last commit also covers every cross-term MMA
+        if (P == 2 && chunk == n_chunks - 1) drain((uint32_t)((2 + (tcount & 1)) * BN));   // the last commit also covers every cross-term MMA
         umma::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (CG == 2) {
             umma::mbar_arrive_cluster(buf ? ae1 : ae0);
-            if (P == 2 && chunk == n_chunks - 1) umma::mbar_arrive_cluster(ce);
+            if (P == 2 && chunk == n_chunks - 1) umma::mbar_arrive_cluster((tcount & 1) ? ce1 : ce0);
           } else {
             umma::mbar_arrive(&acc_empty_bar[buf]);
-            if (P == 2 && chunk == n_chunks - 1) umma::mbar_arrive(cross_empty_bar);
+            if (P == 2 && chunk == n_chunks - 1) umma::mbar_arrive(&cross_empty_bar[tcount & 1]);
           }
         }
       }
@@ -666,11 +702,12 @@ static PFN_cuTensorMapEncodeTiled get_encode_fn() {
 
 static int g_persistent = 1;
 static int g_enable_2cta = 1;
+static int g_weights_resident = 1;
 
-template <int BN, int P, int NX, int CG>
+template <int BN, int P, int NX, int CG, int WR = 0>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
-  using C = ConvCfg<BN, P, NX, CG>;
-  auto kern = k_conv_umma<BN, P, NX, CG>;
+  using C = ConvCfg<BN, P, NX, CG, WR>;
+  auto kern = k_conv_umma<BN, P, NX, CG, WR>;
   static bool configured = false;
   if (!configured) {
     HIMO_CUDA_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
@@ -700,6 +737,8 @@ static int g_disable_halo = 0;
 extern "C" int himo_conv_set_halo(int enable) { g_disable_halo = enable ? 0 : 1; return HIMO_OK; }
 // A/B knob: 0 disables the CTA-pair (cta_group::2) path.
 extern "C" int himo_conv_set_2cta(int enable) { g_enable_2cta = enable ? 1 : 0; return HIMO_OK; }
+// A/B knob: 0 disables the weights-resident variants of the 64-channel encoder layers.
+extern "C" int himo_conv_set_weights_resident(int enable) { g_weights_resident = enable ? 1 : 0; return HIMO_OK; }
 // A/B knob: 0 launches one CTA per tile instead of the persistent one-CTA-per-SM tile loop.
 extern "C" int himo_conv_set_persistent(int enable) { g_persistent = enable ? 1 : 0; return HIMO_OK; }
 // Tuning knob (process-wide): number of hi*hi MMAs (K = 16 each) accumulated in tensor memory before the
@@ -794,6 +833,11 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
   p.aux_h = d->aux_h; p.aux_z = d->aux_z; p.aux_ld = d->aux_ld;
   p.out2 = (__nv_bfloat16*)d->out2; p.out2_plane_stride = d->out2_plane_stride; p.out2_ld = d->out2_ld;
   p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles_n * groups;
+  // weights-resident variants for the 64-channel encoder layers (one N tile, shared by all groups)
+  if (g_weights_resident && BN == 64 && P == 2 && CGsel == 1 && d->Cout == 64 && d->b_group_k_stride == 0 && !d->b_k_total) {
+    if (halo && taps * p.k_chunks == 18) return launch_conv<64, 2, 3, 1, 18>(tmA, tmB, p, stream);
+    if (!halo && taps * p.k_chunks == 9) return launch_conv<64, 2, 1, 1, 9>(tmA, tmB, p, stream);
+  }
 #define HIMO_CONV_CASE(bn, pp)                                                                        \
   if (BN == bn && P == pp) {                                                                          \
     if (CGsel == 2)                                                                                   \

@@ -154,6 +154,9 @@ int himo_conv2d_nhwc(const himo_conv_desc* desc, void* stream);
 int himo_conv_set_flush_iters(int mmas);
 /* A/B knob: 0 disables the haloed-row reuse of the activation tile across the kx taps (default on). */
 int himo_conv_set_halo(int enable);
+/* A/B knob: 0 disables the weights-resident variants (whole weight tensor in shared memory) of the 64-channel
+ * encoder layers (default on). */
+int himo_conv_set_weights_resident(int enable);
 /* A/B knob: 0 launches one CTA per output tile instead of the persistent tile loop (default on). */
 int himo_conv_set_persistent(int enable);
 /* A/B knob: 0 disables the CTA-pair path (tcgen05.mma.cta_group::2 over a cluster of 2; default on). */
