@@ -254,6 +254,11 @@ struct EpiOut {
   long long plane_stride_b;  // bytes between the hi and lo planes (split output)
   float scale;
   int mode;                  // 0 = fp32, 1 = one bf16 plane, 2 = split fp16 planes
+  // optional (FastNSF GEMMs): ReLU-backward mask source (layout of `out`) and transposed split-plane copy
+  const __nv_bfloat16* mask;       // this pixel's first channel of the group, or nullptr
+  long long mask_plane_stride; int mask_planes;
+  __nv_bfloat16* out_t;            // element (first channel of the group, this pixel), or nullptr
+  long long out_t_plane_stride; long long ld_t; int t_planes;
 };
 template <int ACT>
 __device__ __noinline__ void epi_store16(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7,
@@ -271,6 +276,28 @@ __device__ __noinline__ void epi_store16(float a0, float a1, float a2, float a3,
     else if (ACT == 3) v[j] = fast_tanh(x);
     else if (ACT == 4) v[j] = fmaxf(x, 0.f);
     else v[j] = x;
+  }
+  if (o.mask) {   // ReLU backward: pass the gradient where the forward activation was > 0
+    uint32_t mb[8];
+    *(uint4*)&mb[0] = *(const uint4*)o.mask;
+    *(uint4*)&mb[4] = *(const uint4*)(o.mask + 8);
+    if (o.mask_planes == 2) {
+      uint32_t m2[8];
+      *(uint4*)&m2[0] = *(const uint4*)(o.mask + o.mask_plane_stride);
+      *(uint4*)&m2[4] = *(const uint4*)(o.mask + o.mask_plane_stride + 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mb[j] |= m2[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if ((mb[j] & 0x00007fffu) == 0u) v[2 * j] = 0.f;
+      if ((mb[j] & 0x7fff0000u) == 0u) v[2 * j + 1] = 0.f;
+    }
+  }
+  if (o.out_t) {   // transposed copy: element (channel, pixel); the lanes of a warp hold consecutive pixels
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      umma::store_split(o.out_t + j * o.ld_t, o.out_t_plane_stride, o.t_planes, v[j]);
   }
   if (o.mode == 0) {
     float4* dst = (float4*)o.out;
@@ -299,10 +326,14 @@ __device__ __forceinline__ void conv_epilogue_fast(const float* acc, const ConvP
   o.scale = p.acc_scale;
   o.mode = p.out_fp32 ? 0 : (p.out_planes == 2 ? 2 : 1);
   o.plane_stride_b = p.out_plane_stride * 2;
+  o.mask_plane_stride = p.mask_plane_stride; o.mask_planes = p.mask_planes;
+  o.out_t_plane_stride = p.out_t_plane_stride; o.ld_t = p.ld_t; o.t_planes = p.out_planes == 2 ? 2 : 1;
   const long long elem = pix * p.Cout_total + ch0;
 #pragma unroll
   for (int gi = 0; gi < kHalfT / 16; ++gi) {
     o.out = p.out_fp32 ? (void*)((float*)p.out + elem + gi * 16) : (void*)((__nv_bfloat16*)p.out + elem + gi * 16);
+    o.mask = p.mask_src ? p.mask_src + elem + gi * 16 : nullptr;
+    o.out_t = p.out_t ? p.out_t + (ch0 + gi * 16) * (long long)p.ld_t + pix : nullptr;
     const float* a = acc + gi * 16;
     epi_store16<ACT>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14],
                      a[15], bias_s + gi * 16, o);
@@ -590,7 +621,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const long long pix = (long long)py * p.W_out + px + (long long)g * p.out_group_pix_stride;
       const long long ch0 = (long long)p.cout_off + (long long)g * p.cout_group_stride + n0 + half * kHalf;
       const float* bias = p.bias ? p.bias + n0 + half * kHalf : nullptr;
-      if (p.act < 5 && !p.out_t && !p.mask_src && p.Cout <= C::kMaxBias) {
+      if (p.act < 5 && p.Cout <= C::kMaxBias) {
         const float* bias_s = bias_smem + n0 + half * kHalf;
         switch (p.act) {
           case 0: conv_epilogue_fast<0, kHalf>(acc, p, pix, ch0, bias_s); break;
@@ -619,6 +650,168 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (CG == 2) umma::tmem_dealloc_2cta(tmem_base, C::kTmemCols);
     else umma::tmem_dealloc(tmem_base, C::kTmemCols);
   }
+}
+
+// ------------------------------------------------------------------ wide tiles for the 256-channel encoder layers
+// k_conv_wide: 256 output pixels x 256 output channels per CTA pair (cta_group::2, N = 256), split planes,
+// one tap per stage.  The 256->256 layers on 64x64 images were bound by L2->SM operand traffic: with BN = 128
+// every activation tile was fetched once per N tile (64 B/cycle/SM needed, ~42 available).  One N tile halves
+// the activation traffic.  The two accumulators (hi*hi, cross) take all 512 TMEM columns, so there is no
+// ping-pong: the chain is not cut (K/16 <= 144 hi*hi MMAs; the measured flow error stays two orders below the
+// 1e-4 budget) and the epilogue streams TMEM -> activation -> store 16 columns at a time.
+// BK = 64 channels per stage here: 128-byte rows (SWIZZLE_128B), i.e. full-line L2 requests instead of half lines
+constexpr int kWideBK = 64;
+constexpr int kWideRowB = 128;
+constexpr int kWideStageBytes = 2 * 128 * kWideRowB + 2 * 128 * kWideRowB;   // A: 2 planes x 128 px, B: 2 planes x 128 rows
+constexpr int kWideStages = 3;
+constexpr int kWideBarOffset = kWideStages * kWideStageBytes;                // 196608
+constexpr int kWideBiasOffset = kWideBarOffset + 256;
+constexpr int kWideTotal = kWideBiasOffset + 256 * 4 + 1024;    // + 1024-byte alignment slack
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+k_conv_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + kWideBarOffset);
+  uint64_t* empty_bar = full_bar + kWideStages;
+  uint64_t* acc_full_bar = empty_bar + kWideStages;
+  uint64_t* acc_empty_bar = acc_full_bar + 1;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(acc_empty_bar + 1);
+  float* bias_smem = (float*)(smem + kWideBiasOffset);
+  constexpr int kABytes = 128 * kWideRowB, kBBytes = 128 * kWideRowB;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = umma::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int n_workers = (int)(gridDim.x >> 1), worker = (int)(blockIdx.x >> 1);
+  const int k_chunks = p.Cin / kWideBK;
+  const int k_iters = p.taps * k_chunks;
+  if (warp == 0 && lane == 0) {
+    umma::tma_prefetch_desc(&tmA);
+    umma::tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kWideStages; ++s) { umma::mbar_init(&full_bar[s], 1); umma::mbar_init(&empty_bar[s], 1); }
+    umma::mbar_init(acc_full_bar, 1);
+    umma::mbar_init(acc_empty_bar, kConvEpiWarps * 2);
+    umma::fence_barrier_init();
+  } else if (warp == 1) {
+    umma::tmem_alloc_2cta(tmem_ptr_smem, 512);
+  }
+  for (int i = threadIdx.x; i < 256; i += kConvThreads) bias_smem[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int m_tiles = p.tiles_x * p.tiles_y;
+  const int total_work = (m_tiles >> 1) * p.n_groups;
+  auto decode = [&](int t, int& g, int& x0, int& y0) {
+    const int m = (t % (m_tiles >> 1)) * 2 + (int)cta_rank;
+    g = t / (m_tiles >> 1);
+    x0 = (m % p.tiles_x) * p.TW; y0 = (m / p.tiles_x) * p.TH;
+  };
+
+  if (warp == 0) {
+    uint32_t git = 0;
+    for (int tile = worker; tile < total_work; tile += n_workers) {
+      int g, x0, y0;
+      decode(tile, g, x0, y0);
+      const int cin0 = p.cin_off + g * p.cin_group_stride;
+      for (int it = 0; it < k_iters; ++it, ++git) {
+        const int s = git % kWideStages;
+        umma::mbar_wait(&empty_bar[s], ((git / kWideStages) & 1) ^ 1);
+        const uint32_t fb = umma::mapa_u32(umma::smem_u32(&full_bar[s]), 0);
+        uint8_t* a_dst = smem + s * kWideStageBytes;
+        uint8_t* b_dst = a_dst + 2 * kABytes;
+        if (umma::elect_one()) {
+          if (leader) umma::mbar_arrive_expect_tx(&full_bar[s], kWideStageBytes * 2);
+          const int tap = it / k_chunks, kc = it - tap * k_chunks;
+          const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl)
+            umma::tma_load_4d_2cta(a_dst + pl * kABytes, &tmA, fb, cin0 + kc * kWideBK, x0 * p.stride + kx - p.pad,
+                                   y0 * p.stride + ky - p.pad, pl);
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl)
+            umma::tma_load_3d_2cta(b_dst + pl * kBBytes, &tmB, fb, tap * p.Cin + kc * kWideBK, (int)cta_rank * 128, pl);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      constexpr uint32_t idesc = umma::idesc_f16kind_f32(256, 256, 0u, 0u);
+      uint32_t git = 0, tcount = 0;
+      for (int tile = worker; tile < total_work; tile += n_workers, ++tcount) {
+        umma::mbar_wait(acc_empty_bar, (tcount & 1) ^ 1);     // both CTAs' epilogues have streamed the previous tile out
+        umma::tc_fence_after();
+        for (int it = 0; it < k_iters; ++it, ++git) {
+          const int s = git % kWideStages;
+          umma::mbar_wait(&full_bar[s], (git / kWideStages) & 1);
+          umma::tc_fence_after();
+          const uint32_t a_addr = umma::smem_u32(smem + s * kWideStageBytes), b_addr = a_addr + 2 * kABytes;
+          if (umma::elect_one()) {
+            const uint64_t a_hi = umma::smem_desc_kmajor<kWideRowB>(a_addr), a_lo = umma::smem_desc_kmajor<kWideRowB>(a_addr + kABytes);
+            const uint64_t b_hi = umma::smem_desc_kmajor<kWideRowB>(b_addr), b_lo = umma::smem_desc_kmajor<kWideRowB>(b_addr + kBBytes);
+#pragma unroll
+            for (int k = 0; k < kWideBK / 16; ++k) {
+              const uint64_t koff = (uint64_t)(k * 32 >> 4);
+              umma::mma_bf16_ss_2cta(tmem_base, a_hi + koff, b_hi + koff, idesc, (it | k) != 0 ? 1u : 0u);
+              umma::mma_bf16_ss_2cta(tmem_base + 256, a_hi + koff, b_lo + koff, idesc, (it | k) != 0 ? 1u : 0u);
+              umma::mma_bf16_ss_2cta(tmem_base + 256, a_lo + koff, b_hi + koff, idesc, 1u);
+            }
+            umma::mma_commit_2cta(&empty_bar[s]);
+          }
+          __syncwarp();
+        }
+        if (umma::elect_one()) umma::mma_commit_2cta(acc_full_bar);
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2, row = q * 32 + lane;
+    const uint32_t lane_col = ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+    const uint32_t ae = umma::mapa_u32(umma::smem_u32(acc_empty_bar), 0);
+    uint32_t tcount = 0;
+    for (int tile = worker; tile < total_work; tile += n_workers, ++tcount) {
+      int g, x0, y0;
+      decode(tile, g, x0, y0);
+      const int py = y0 + row / p.TW, px = x0 + row % p.TW;
+      const long long pix = (long long)py * p.W_out + px;
+      const long long ch0 = (long long)p.cout_off + (long long)g * p.cout_group_stride + half * 128;
+      EpiOut o;
+      o.scale = p.acc_scale;
+      o.mode = p.out_fp32 ? 0 : (p.out_planes == 2 ? 2 : 1);
+      o.plane_stride_b = p.out_plane_stride * 2;
+      o.mask = nullptr; o.mask_plane_stride = 0; o.mask_planes = 0;
+      o.out_t = nullptr; o.out_t_plane_stride = 0; o.ld_t = 0; o.t_planes = 1;
+      const long long elem = pix * p.Cout_total + ch0;
+      umma::mbar_wait(acc_full_bar, tcount & 1);
+      umma::tc_fence_after();
+#pragma unroll 1
+      for (int gi = 0; gi < 8; ++gi) {
+        uint32_t m[16], c[16];
+        umma::tmem_ld_32x16(tmem_base + lane_col + (uint32_t)(gi * 16), m);
+        umma::tmem_ld_32x16(tmem_base + lane_col + (uint32_t)(256 + gi * 16), c);
+        umma::tmem_ld_wait();
+        float a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = __uint_as_float(m[j]) + __uint_as_float(c[j]);
+        o.out = p.out_fp32 ? (void*)((float*)p.out + elem + gi * 16) : (void*)((__nv_bfloat16*)p.out + elem + gi * 16);
+        const float* bs = bias_smem + half * 128 + gi * 16;
+        if (p.act == 1)
+          epi_store16<1>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15], bs, o);
+        else
+          epi_store16<0>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15], bs, o);
+      }
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive_cluster(ae);
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync();
+  if (warp == 1) umma::tmem_dealloc_2cta(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------ bilinear 2x upsample
@@ -703,6 +896,7 @@ static PFN_cuTensorMapEncodeTiled get_encode_fn() {
 static int g_persistent = 1;
 static int g_enable_2cta = 1;
 static int g_weights_resident = 1;
+static int g_wide_tiles = 1;
 
 template <int BN, int P, int NX, int CG, int WR = 0>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
@@ -737,6 +931,8 @@ static int g_disable_halo = 0;
 extern "C" int himo_conv_set_halo(int enable) { g_disable_halo = enable ? 0 : 1; return HIMO_OK; }
 // A/B knob: 0 disables the CTA-pair (cta_group::2) path.
 extern "C" int himo_conv_set_2cta(int enable) { g_enable_2cta = enable ? 1 : 0; return HIMO_OK; }
+// A/B knob: 0 disables the 256-wide N tiles (k_conv_wide) of the 256-channel encoder layers.
+extern "C" int himo_conv_set_wide_tiles(int enable) { g_wide_tiles = enable ? 1 : 0; return HIMO_OK; }
 // A/B knob: 0 disables the weights-resident variants of the 64-channel encoder layers.
 extern "C" int himo_conv_set_weights_resident(int enable) { g_weights_resident = enable ? 1 : 0; return HIMO_OK; }
 // A/B knob: 0 launches one CTA per tile instead of the persistent one-CTA-per-SM tile loop.
@@ -833,6 +1029,46 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
   p.aux_h = d->aux_h; p.aux_z = d->aux_z; p.aux_ld = d->aux_ld;
   p.out2 = (__nv_bfloat16*)d->out2; p.out2_plane_stride = d->out2_plane_stride; p.out2_ld = d->out2_ld;
   p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles_n * groups;
+  // 256-channel layers on short rows: one 256-wide N tile per CTA pair (k_conv_wide)
+  if (g_wide_tiles && P == 2 && d->Cout == 256 && d->Cin % kWideBK == 0 && !halo && m_tiles_total % 2 == 0 && (d->act == 0 || d->act == 1) &&
+      !d->out_t && !d->mask_src && !d->stop_flag && d->b_group_k_stride == 0 && !d->b_k_total) {
+    CUtensorMap tmBw, tmAw;
+    cuuint64_t dimsw[3] = {(cuuint64_t)k_total, (cuuint64_t)d->Cout, 2};
+    cuuint64_t stridesw[2] = {(cuuint64_t)k_total * 2, (cuuint64_t)d->Cout * k_total * 2};
+    cuuint32_t boxw[3] = {(cuuint32_t)kWideBK, 128, 1};
+    cuuint32_t estrw[3] = {1, 1, 1};
+    if (enc(&tmBw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d->wgt, dimsw, stridesw, boxw, estrw,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return HIMO_ERR_ARG;
+    {
+      cuuint64_t dimsa[4] = {(cuuint64_t)d->Cin_total, (cuuint64_t)d->W_in, (cuuint64_t)d->H_in, (cuuint64_t)P};
+      cuuint64_t stridesa[3] = {(cuuint64_t)d->Cin_total * 2, (cuuint64_t)d->W_in * d->Cin_total * 2,
+                                (cuuint64_t)d->in_plane_stride * 2};
+      cuuint32_t boxa[4] = {(cuuint32_t)kWideBK, (cuuint32_t)((TW - 1) * d->stride + 1), (cuuint32_t)((TH - 1) * d->stride + 1), 1};
+      cuuint32_t estra[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+      if (enc(&tmAw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)d->in, dimsa, stridesa, boxa, estra,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return HIMO_ERR_ARG;
+    }
+    static bool wide_configured = false;
+    if (!wide_configured) {
+      HIMO_CUDA_RET(cudaFuncSetAttribute(k_conv_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideTotal));
+      wide_configured = true;
+    }
+    const int work = (m_tiles_total / 2) * groups;
+    const int pairs = work < kNumSMs / 2 ? work : kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pairs * 2); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = kWideTotal; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    HIMO_CUDA_RET(cudaLaunchKernelEx(&cfg, k_conv_wide, tmAw, tmBw, p));
+    HIMO_LAUNCH_RET();
+    return HIMO_OK;
+  }
   // weights-resident variants for the 64-channel encoder layers (one N tile, shared by all groups)
   if (g_weights_resident && BN == 64 && P == 2 && CGsel == 1 && d->Cout == 64 && d->b_group_k_stride == 0 && !d->b_k_total) {
     if (halo && taps * p.k_chunks == 18) return launch_conv<64, 2, 3, 1, 18>(tmA, tmB, p, stream);
