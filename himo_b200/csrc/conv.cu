@@ -897,6 +897,7 @@ static int g_persistent = 1;
 static int g_enable_2cta = 1;
 static int g_weights_resident = 1;
 static int g_wide_tiles = 1;
+static int g_pair_min_mmas = 48;
 
 template <int BN, int P, int NX, int CG, int WR = 0>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
@@ -931,6 +932,8 @@ static int g_disable_halo = 0;
 extern "C" int himo_conv_set_halo(int enable) { g_disable_halo = enable ? 0 : 1; return HIMO_OK; }
 // A/B knob: 0 disables the CTA-pair (cta_group::2) path.
 extern "C" int himo_conv_set_2cta(int enable) { g_enable_2cta = enable ? 1 : 0; return HIMO_OK; }
+// Tuning knob: CTA pairs are used when a tile carries at least this many hi*hi MMAs (default 48).
+extern "C" int himo_conv_set_pair_min_mmas(int n) { g_pair_min_mmas = n; return HIMO_OK; }
 // A/B knob: 0 disables the 256-wide N tiles (k_conv_wide) of the 256-channel encoder layers.
 extern "C" int himo_conv_set_wide_tiles(int enable) { g_wide_tiles = enable ? 1 : 0; return HIMO_OK; }
 // A/B knob: 0 disables the weights-resident variants of the 64-channel encoder layers.
@@ -978,7 +981,7 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
   // (measured: pairing pays once a tile carries >= ~48 hi*hi MMAs; below that the pair's lock-step costs more
   // than the halved weight traffic saves)
   const int main_mmas_per_tile = d->ksize * d->ksize * (d->Cin / BK) * 2;
-  const int CGsel = (g_enable_2cta && m_tiles_total % 2 == 0 && main_mmas_per_tile >= 48) ? 2 : 1;
+  const int CGsel = (g_enable_2cta && m_tiles_total % 2 == 0 && main_mmas_per_tile >= g_pair_min_mmas) ? 2 : 1;
   // halo mode: 3x3, stride 1, full 128-pixel row tiles -> one haloed A load feeds the three kx taps
   const bool halo = d->ksize == 3 && d->stride == 1 && TW == 128 && TH == 1 && !g_disable_halo;
   PFN_cuTensorMapEncodeTiled enc = get_encode_fn();

@@ -19,8 +19,10 @@
 
 namespace himo {
 
-constexpr int kNNMaxBits = 26;                                   // key space: 2^26 cells = 8 MiB bitmap per cloud
-constexpr long long kNNMaxWords = (1ll << kNNMaxBits) / 64 + 1;  // 64-bit words (+1 so rank(n_cells) exists)
+// key space: 2^26 cells (8 MiB bitmap per cloud) up to 400 k points in total, 2^28 beyond -- dense million-point
+// clouds want 0.125 m cells (1M-point lidar pair: 5.8 ms at 0.25 m, 3.8 ms at 0.125 m)
+__host__ __device__ inline int nn_max_bits(long long n_total) { return n_total < 400000 ? 26 : 28; }
+__host__ __device__ inline long long nn_max_words(long long n_total) { return (1ll << nn_max_bits(n_total)) / 64 + 1; }
 constexpr int kNNLeaf = 128;   // nodes with <= this many points are scanned: expanding a node costs ~50 point tests
 
 struct NNGrid {
@@ -117,7 +119,7 @@ __device__ __forceinline__ int ceil_log2_i(long long v) {
 
 // grid = robust box (mean +- 4 sigma clipped to the bounding box), cell edge doubled until the Morton key
 // space 2^(2*bxy + bz) fits the bitmap
-__global__ void k_nn_params(const NNStats* __restrict__ st, float cell, NNGrid* __restrict__ g) {
+__global__ void k_nn_params(const NNStats* __restrict__ st, float cell, int max_bits, NNGrid* __restrict__ g) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
   float amax = 0.f;
@@ -143,7 +145,7 @@ __global__ void k_nn_params(const NNStats* __restrict__ st, float cell, NNGrid* 
     bxy = ceil_log2_i(cx > cy ? cx : cy);
     bz = ceil_log2_i(cz);
     if (bz > bxy) bxy = bz;
-    if (2 * bxy + bz <= kNNMaxBits && bxy <= 13 && bz <= 10) break;
+    if (2 * bxy + bz <= max_bits && bxy <= 13 && bz <= 10) break;
     h *= 2.f;
   }
   g->ox = lo[0]; g->oy = lo[1]; g->oz = lo[2];
@@ -333,8 +335,8 @@ __device__ __forceinline__ void nn_descend(const NNGrid& g, const NNRef& r, NNQu
                                            unsigned* stack, int sp) {
   while (sp > 0) {
     const unsigned ent = stack[--sp];
-    const unsigned base = ent & ((1u << 27) - 1u);
-    const int lvl = (int)(ent >> 27);
+    const unsigned base = ent & ((1u << 28) - 1u);      // keys have up to 28 bits, levels <= 13
+    const int lvl = (int)(ent >> 28);
     int cx, cy, cz;
     nn_unkey(g, base, cx, cy, cz);
     if (nn_box_d2(g, q, lvl, cx >> lvl, cy >> lvl, cz >> lvl) > q.best) continue;
@@ -372,7 +374,7 @@ __device__ __forceinline__ void nn_descend(const NNGrid& g, const NNRef& r, NNQu
       if (sz) iz = (mm & 1) ^ nz_;
       if ((ix ? ax[1] : ax[0]) + (iy ? ay[1] : ay[0]) + (iz ? az[1] : az[0]) > q.best) continue;
       const unsigned ckey = base | (ix ? bx : 0u) | (iy ? bx << 1 : 0u) | (iz ? bzb : 0u);
-      if (sp < 96) stack[sp++] = ckey | ((unsigned)cl << 27);
+      if (sp < 96) stack[sp++] = ckey | ((unsigned)cl << 28);
       else {   // cannot happen (depth <= 13, <= 7 pending siblings per level); scan rather than drop
         int cs, ce;
         nn_node_range(g, r, ckey, cl, cs, ce);
@@ -476,7 +478,7 @@ k_nn_search(NNCloud c0, NNCloud c1, const NNGrid* __restrict__ gp, float* __rest
           nn_node_range(g, r, base, lvl, s, e);
           if (s == e) continue;
           if (e - s > kNNLeaf) {                              // big node: depth-first, nearest child first
-            stack[0] = base | ((unsigned)lvl << 27);
+            stack[0] = base | ((unsigned)lvl << 28);
             nn_descend(g, r, q, cx, cy, cz, stack, 1);
             continue;
           }
@@ -526,7 +528,7 @@ k_chamfer_grad(const float* __restrict__ a, int na, const float* __restrict__ b,
   }
 }
 
-static size_t nn_cloud_bytes(int n) {
+static size_t nn_cloud_bytes(int n, long long kNNMaxWords) {
   size_t m = (size_t)(n > 0 ? n : 1);
   size_t b = 0;
   b += align_up(m * sizeof(unsigned), 256);                       // keys
@@ -547,7 +549,8 @@ using namespace himo;
 
 extern "C" size_t himo_chamfer_workspace_bytes(int n0, int n1) {
   if (n0 < 0 || n1 < 0) return 0;
-  return nn_cloud_bytes(n0) + nn_cloud_bytes(n1) + 4096 + 16 * 256;
+  const long long mw = nn_max_words((long long)n0 + n1);
+  return nn_cloud_bytes(n0, mw) + nn_cloud_bytes(n1, mw) + 4096 + 16 * 256;
 }
 
 static int nn_forward_impl(const float* pc0, int n0, const float* pc1, int n1, float* dist0,
@@ -562,9 +565,10 @@ static int nn_forward_impl(const float* pc0, int n0, const float* pc1, int n1, f
     if (n1 > 0) { k_nn_fill_empty<<<ceil_div(n1, 256), 256, 0, stream>>>(dist1, idx1, n1); HIMO_LAUNCH_RET(); }
     return HIMO_OK;
   }
-  // default finest cell: about the point spacing -- 0.5 m up to a few hundred thousand points, 0.25 m beyond
+  // default finest cell: about the point spacing -- 0.5 m up to a few hundred thousand points, 0.125 m beyond
   // (measured: 0.5 m is 4-20 % faster at 100 k points per cloud; coarser levels come for free from the key)
-  if (!(cell_size > 0.f)) cell_size = ((long long)n0 + n1 < 400000) ? 0.5f : 0.25f;
+  if (!(cell_size > 0.f)) cell_size = ((long long)n0 + n1 < 400000) ? 0.5f : 0.125f;
+  const long long kNNMaxWords = nn_max_words((long long)n0 + n1);
   Arena A(workspace, workspace_bytes);
   NNStats* stats = A.take<NNStats>(1);
   NNGrid* grid = A.take<NNGrid>(1);
@@ -593,7 +597,7 @@ static int nn_forward_impl(const float* pc0, int n0, const float* pc1, int n1, f
   HIMO_LAUNCH_RET();
   k_nn_stats<<<min(ceil_div(n0 + n1, 256), kNumSMs * 2), 256, 0, stream>>>(pc0, n0, pc1, n1, stats);
   HIMO_LAUNCH_RET();
-  k_nn_params<<<1, 32, 0, stream>>>(stats, cell_size, grid);
+  k_nn_params<<<1, 32, 0, stream>>>(stats, cell_size, nn_max_bits((long long)n0 + n1), grid);
   HIMO_LAUNCH_RET();
   const int nmax = n0 > n1 ? n0 : n1;
   dim3 grid2(min(ceil_div(nmax, 256), kNumSMs * 8), 2);
