@@ -52,6 +52,9 @@ struct EmbedArgs {
   float* voxel_feats;   // [F][n_max][32] fp32 voxel features in sorted-voxel order
   float* voxel_mean;    // [F][n_max][3] (optional, may be null)
   int* voxel_key;       // [F][n_max] cell key of each voxel (optional, may be null)
+  int* big_count;       // [F] number of crowded pillars (> kPfnBigVoxel points), zeroed per call
+  int* big_list;        // [F][n_max / kPfnBigVoxel + 1] their voxel indices, in arrival order
+  int big_stride;
   __nv_bfloat16* canvas;       // [planes][gy][gx][F*32]
   int canvas_planes;
   long long canvas_plane_stride;
@@ -181,6 +184,11 @@ k_embed_fill(EmbedArgs a) {
   }
 }
 
+// Pillars with more points than this are handled by a whole block (k_embed_pfn_big).  Near the sensor a pillar
+// holds 500-750 points of a 100 k-point sweep; walked by one warp (4 points per dependent-load round) the largest
+// pillar alone set the kernel time (~100 us), although 140 such pillars hold only a third of the points.
+constexpr int kPfnBigVoxel = 128;
+
 // One warp per voxel, lane = output feature channel.
 __global__ void __launch_bounds__(256)
 k_embed_pfn(EmbedArgs a, EmbedGrid g) {
@@ -198,6 +206,10 @@ k_embed_pfn(EmbedArgs a, EmbedGrid g) {
   const int C = a.n_frames * 32;
   for (int v = blockIdx.x * warps_per_block + (threadIdx.x >> 5); v < m; v += gridDim.x * warps_per_block) {
     const int beg = seg[v], end = seg[v + 1], cnt = end - beg;
+    if (cnt > kPfnBigVoxel) {                    // k_embed_pfn_big: one block per crowded pillar
+      if (lane == 0) a.big_list[(size_t)f * a.big_stride + atomicAdd(a.big_count + f, 1)] = v;
+      continue;
+    }
     // voxel mean of xyz: double accumulation (order-free up to the final rounding), then an fp32
     // divide by the fp32 count as scatter_points_cuda.cu:59-60 does
     double sx = 0.0, sy = 0.0, sz = 0.0;
@@ -256,6 +268,95 @@ k_embed_pfn(EmbedArgs a, EmbedGrid g) {
   }
 }
 
+// Crowded pillars: one block (8 warps) per voxel.  The mean is a block-wide strided double sum, the PFN sum is
+// split into 8 contiguous point ranges (one per warp, lane = channel, 4 independent accumulators) whose partials
+// are added in warp order -- fixed association, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(256)
+k_embed_pfn_big(EmbedArgs a, EmbedGrid g) {
+  __shared__ double s_mean[8][3];
+  __shared__ double s_part[8][32];
+  __shared__ int s_key;
+  const int f = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = a.num_voxels[f];
+  const float4* pt4 = a.pt4 + (size_t)f * a.n_max;
+  const int* seg = a.seg_start + (size_t)f * (a.n_max + 1);
+  const int* sorted_idx = a.sorted_idx + (size_t)f * a.n_max;
+  float w[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w[k] = __ldg(a.pfn_w + lane * 9 + k);
+  const float b = __ldg(a.pfn_b + lane);
+  const int C = a.n_frames * 32;
+  // the crowded pillars were listed by k_embed_pfn (arrival order; every pillar's result is independent of it)
+  const int nbig = a.big_count[f];
+  const int* list = a.big_list + (size_t)f * a.big_stride;
+  {
+  for (int li = blockIdx.x; li < nbig; li += gridDim.x) {
+    const int v = list[li];
+    const int beg = seg[v], end = seg[v + 1], cnt = end - beg;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int k = beg + threadIdx.x; k < end; k += 256) {
+      const float4 p = pt4[sorted_idx[k]];
+      sx += (double)p.x; sy += (double)p.y; sz += (double)p.z;
+      if (k == beg) s_key = __float_as_int(p.w);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, d);
+      sy += __shfl_xor_sync(0xffffffffu, sy, d);
+      sz += __shfl_xor_sync(0xffffffffu, sz, d);
+    }
+    if (lane == 0) { s_mean[warp][0] = sx; s_mean[warp][1] = sy; s_mean[warp][2] = sz; }
+    __syncthreads();
+    sx = 0.0; sy = 0.0; sz = 0.0;
+    for (int wv = 0; wv < 8; ++wv) { sx += s_mean[wv][0]; sy += s_mean[wv][1]; sz += s_mean[wv][2]; }
+    const int key = s_key;
+    const float fc = (float)cnt;
+    const float mx = __fdiv_rn((float)sx, fc), my = __fdiv_rn((float)sy, fc), mz = __fdiv_rn((float)sz, fc);
+    const int cy = key / g.gx, cx = key - cy * g.gx;
+    const float ccx = __fadd_rn(__fmul_rn((float)cx, g.vx), g.x_off);
+    const float ccy = __fadd_rn(__fmul_rn((float)cy, g.vy), g.y_off);
+    const float ccz = __fadd_rn(__fmul_rn(0.f, g.vz), g.z_off);
+    auto pfn_point = [&](const float4 p) -> double {
+      float y = w[0] * p.x;
+      y = fmaf(w[1], p.y, y);
+      y = fmaf(w[2], p.z, y);
+      y = fmaf(w[3], p.x - mx, y);
+      y = fmaf(w[4], p.y - my, y);
+      y = fmaf(w[5], p.z - mz, y);
+      y = fmaf(w[6], p.x - ccx, y);
+      y = fmaf(w[7], p.y - ccy, y);
+      y = fmaf(w[8], p.z - ccz, y);
+      y += b;
+      return (double)fmaxf(y, 0.f);
+    };
+    const int per = (cnt + 7) / 8;
+    const int wb = beg + warp * per, we = min(wb + per, end);
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int k = wb;
+    for (; k + 4 <= we; k += 4) {
+      const int i0 = sorted_idx[k], i1 = sorted_idx[k + 1], i2 = sorted_idx[k + 2], i3 = sorted_idx[k + 3];
+      const float4 p0 = pt4[i0], p1 = pt4[i1], p2 = pt4[i2], p3 = pt4[i3];
+      acc0 += pfn_point(p0); acc1 += pfn_point(p1); acc2 += pfn_point(p2); acc3 += pfn_point(p3);
+    }
+    for (; k < we; ++k) acc0 += pfn_point(pt4[sorted_idx[k]]);
+    s_part[warp][lane] = (acc0 + acc1) + (acc2 + acc3);
+    __syncthreads();
+    if (warp == 0) {
+      double acc = 0.0;
+      for (int wv = 0; wv < 8; ++wv) acc += s_part[wv][lane];
+      const float feat = __fdiv_rn((float)acc, fc);
+      a.voxel_feats[((size_t)f * a.n_max + v) * 32 + lane] = feat;
+      if (a.voxel_mean && lane < 3)
+        a.voxel_mean[((size_t)f * a.n_max + v) * 3 + lane] = lane == 0 ? mx : (lane == 1 ? my : mz);
+      if (a.voxel_key && lane == 0) a.voxel_key[(size_t)f * a.n_max + v] = key;
+      umma::store_split(a.canvas + (size_t)key * C + f * 32 + lane, a.canvas_plane_stride, a.canvas_planes, feat);
+    }
+    __syncthreads();
+  }
+  }
+}
+
 }  // namespace himo
 
 using namespace himo;
@@ -275,10 +376,14 @@ static inline size_t embed_ws_layout(int n_frames, int n_max, int n_words, Embed
   float* vfeat = A.take<float>(F * N * 32);
   float* vmean = A.take<float>(F * N * 3);
   int* vkey = A.take<int>(F * N);
+  const size_t big_stride = N / kPfnBigVoxel + 1;
+  int* big_count = A.take<int>(F);
+  int* big_list = A.take<int>(F * big_stride);
   if (a) {
     a->pt4 = pt4; a->bitmap = bitmap; a->count = count; a->word_prefix = word_prefix;
     a->num_voxels = num_voxels; a->rank = rank; a->slot = slot; a->seg_start = seg;
     a->sorted_idx = sorted_idx; a->voxel_feats = vfeat; a->voxel_mean = vmean; a->voxel_key = vkey;
+    a->big_count = big_count; a->big_list = big_list; a->big_stride = (int)big_stride;
   }
   return A.off + 256;
 }
@@ -333,6 +438,7 @@ extern "C" int himo_embed_frames(const himo_embed_desc* d, void* stream_) {
   const size_t F = (size_t)d->n_frames, N = (size_t)(d->n_max > 0 ? d->n_max : 1);
   HIMO_CUDA_RET(cudaMemsetAsync(a.bitmap, 0, F * a.n_words * sizeof(unsigned), stream));
   HIMO_CUDA_RET(cudaMemsetAsync(a.count, 0, F * (N + 1) * sizeof(int), stream));
+  HIMO_CUDA_RET(cudaMemsetAsync(a.big_count, 0, F * sizeof(int), stream));
   if (!d->skip_canvas_clear)
     HIMO_CUDA_RET(cudaMemsetAsync(a.canvas, 0, (size_t)a.canvas_plane_stride * d->canvas_planes * 2, stream));
   if (n_max > 0) {
@@ -349,6 +455,8 @@ extern "C" int himo_embed_frames(const himo_embed_desc* d, void* stream_) {
     HIMO_LAUNCH_RET();
     dim3 gv(kNumSMs * 4, d->n_frames);
     k_embed_pfn<<<gv, 256, 0, stream>>>(a, g);
+    HIMO_LAUNCH_RET();
+    k_embed_pfn_big<<<dim3(kNumSMs * 2, d->n_frames), 256, 0, stream>>>(a, g);
     HIMO_LAUNCH_RET();
   } else {
     HIMO_CUDA_RET(cudaMemsetAsync(a.num_voxels, 0, F * sizeof(int), stream));
