@@ -48,6 +48,7 @@ struct ConvParams {
   int act, out_fp32;
   float acc_scale;
   int flush_stages;
+  int a_tmem;                        // split mode: stage the A slices in tensor memory (tcgen05.cp + .ts MMAs)
   // GEMM-epilogue extensions used by the FastNSF MLP (csrc/nsf.cu)
   __nv_bfloat16* out_t;            // optional transposed copy: [planes][Cout_total][ld_t], column = pixel
   long long out_t_plane_stride;
@@ -110,7 +111,11 @@ struct ConvCfg {
   static constexpr int kBiasOffset = kBarOffset + 512;               // fp32 bias vector staged once per CTA
   static constexpr int kMaxBias = 1024;
   static constexpr int kTotal = kBiasOffset + kMaxBias * 4 + 128;   // barriers + bias + alignment slack
-  static constexpr int kUsedCols = P == 2 ? 4 * BN : 2 * BN;         // split mode: 2 main + 2 cross accumulators
+  // split mode: 2 main + 1 or 2 cross accumulators, then 8 staging slots x 16 columns for the A slices in TMEM
+  static constexpr int kCrossBufs = (P == 2 && 4 * BN + 128 <= 512) ? 2 : 1;
+  static constexpr int kAccCols = P == 2 ? (2 + kCrossBufs) * BN : 2 * BN;
+  static constexpr int kStageCol = kAccCols;
+  static constexpr int kUsedCols = P == 2 ? kAccCols + 128 : kAccCols;
   static constexpr int kTmemCols = kUsedCols <= 64 ? 64 : kUsedCols <= 128 ? 128 : kUsedCols <= 256 ? 256 : 512;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
@@ -505,13 +510,14 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (CG == 2) umma::mma_commit_2cta(bar);
         else umma::mma_commit(bar);
       };
-      uint32_t git = 0, gch = 0, tcount = 0;
+      uint32_t git = 0, gch = 0, tcount = 0, ts_slot = 0;
       if (WR > 0) { umma::mbar_wait(bres_bar, 0); umma::tc_fence_after(); }
       const uint32_t bres_addr = umma::smem_u32(smem + C::kBResOffset);
       for (int tile = worker; tile < total_work; tile += n_workers, ++tcount) {
-        const uint32_t tmem_cross = tmem_base + (2 + (tcount & 1)) * BN;
-        if (P == 2) {   // the epilogue must have read this cross accumulator's previous tile (two tiles ago)
-          umma::mbar_wait(&cross_empty_bar[tcount & 1], ((tcount >> 1) & 1) ^ 1);
+        const uint32_t xb = C::kCrossBufs == 2 ? (tcount & 1) : 0u;
+        const uint32_t tmem_cross = tmem_base + (2 + xb) * BN;
+        if (P == 2) {   // the epilogue must have read this cross accumulator's previous use
+          umma::mbar_wait(&cross_empty_bar[xb], (C::kCrossBufs == 2 ? ((tcount >> 1) & 1) : (tcount & 1)) ^ 1);
           umma::tc_fence_after();
         }
         int it = 0;
@@ -546,6 +552,27 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int k = 0; k < kConvBK / 16; ++k) {
                 const uint64_t koff = (uint64_t)(k * 32 >> 4);  // 16 elements = 32 bytes along K
+                if (P == 2 && p.a_tmem) {
+                  // A slices through tensor memory: a_hi is read from shared memory once for its two products
+                  // (SS MMAs read 18 KB of operands per k-step and SM, this form 14 KB -- the shared-memory
+                  // bandwidth is what bounds these MMAs, profiles/r01_enc1_smem_bandwidth.txt)
+                  const uint32_t ta = tmem_base + C::kStageCol + (ts_slot & 7u) * 16u;
+                  ++ts_slot;
+                  if (CG == 2) {
+                    umma::tmem_cp_128x256b_2cta(ta, a_hi + koff);
+                    umma::tmem_cp_128x256b_2cta(ta + 8, a_lo + koff);
+                    umma::mma_f16_ts_2cta(tmem_main, ta, b_hi + koff, idesc, (it != it_begin || kx != 0 || k != 0) ? 1u : 0u);
+                    umma::mma_f16_ts_2cta(tmem_cross, ta, b_lo + koff, idesc, (it | kx | k) != 0 ? 1u : 0u);
+                    umma::mma_f16_ts_2cta(tmem_cross, ta + 8, b_hi + koff, idesc, 1u);
+                  } else {
+                    umma::tmem_cp_128x256b(ta, a_hi + koff);
+                    umma::tmem_cp_128x256b(ta + 8, a_lo + koff);
+                    umma::mma_f16_ts(tmem_main, ta, b_hi + koff, idesc, (it != it_begin || kx != 0 || k != 0) ? 1u : 0u);
+                    umma::mma_f16_ts(tmem_cross, ta, b_lo + koff, idesc, (it | kx | k) != 0 ? 1u : 0u);
+                    umma::mma_f16_ts(tmem_cross, ta + 8, b_hi + koff, idesc, 1u);
+                  }
+                  continue;
+                }
                 mma(tmem_main, a_hi + koff, b_hi + koff, idesc, (it != it_begin || kx != 0 || k != 0) ? 1u : 0u);
                 if (P == 2) {   // hi*lo + lo*hi (lo*lo ~ 2^-22 relative is dropped)
                   mma(tmem_cross, a_hi + koff, b_lo + koff, idesc, (it | kx | k) != 0 ? 1u : 0u);
@@ -601,16 +628,17 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         };
         drain((uint32_t)(buf * BN));
-        if (P == 2 && chunk == n_chunks - 1) drain((uint32_t)((2 + (tcount & 1)) * BN));   // the last commit also covers every cross-term MMA
+        const uint32_t xb = C::kCrossBufs == 2 ? (tcount & 1) : 0u;
+        if (P == 2 && chunk == n_chunks - 1) drain((uint32_t)((2 + xb) * BN));   // the last commit also covers every cross-term MMA
         umma::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (CG == 2) {
             umma::mbar_arrive_cluster(buf ? ae1 : ae0);
-            if (P == 2 && chunk == n_chunks - 1) umma::mbar_arrive_cluster((tcount & 1) ? ce1 : ce0);
+            if (P == 2 && chunk == n_chunks - 1) umma::mbar_arrive_cluster(xb ? ce1 : ce0);
           } else {
             umma::mbar_arrive(&acc_empty_bar[buf]);
-            if (P == 2 && chunk == n_chunks - 1) umma::mbar_arrive(&cross_empty_bar[tcount & 1]);
+            if (P == 2 && chunk == n_chunks - 1) umma::mbar_arrive(&cross_empty_bar[xb]);
           }
         }
       }
@@ -898,6 +926,7 @@ static int g_enable_2cta = 1;
 static int g_weights_resident = 1;
 static int g_wide_tiles = 1;
 static int g_pair_min_mmas = 48;
+static int g_a_tmem = 0;   // measured neutral on the 128-wide layers, slower on the 64-wide ones (profiles/r01_conv_a_tmem_ab.txt)
 
 template <int BN, int P, int NX, int CG, int WR = 0>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
@@ -932,6 +961,8 @@ static int g_disable_halo = 0;
 extern "C" int himo_conv_set_halo(int enable) { g_disable_halo = enable ? 0 : 1; return HIMO_OK; }
 // A/B knob: 0 disables the CTA-pair (cta_group::2) path.
 extern "C" int himo_conv_set_2cta(int enable) { g_enable_2cta = enable ? 1 : 0; return HIMO_OK; }
+// A/B knob: 0 reads both MMA operands from shared memory (SS form) instead of staging A in tensor memory.
+extern "C" int himo_conv_set_a_tmem(int enable) { g_a_tmem = enable ? 1 : 0; return HIMO_OK; }
 // Tuning knob: CTA pairs are used when a tile carries at least this many hi*hi MMAs (default 48).
 extern "C" int himo_conv_set_pair_min_mmas(int n) { g_pair_min_mmas = n; return HIMO_OK; }
 // A/B knob: 0 disables the 256-wide N tiles (k_conv_wide) of the 256-channel encoder layers.
@@ -1024,6 +1055,7 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
     const int per_stage = 2 * (halo ? 3 : 1);
     p.flush_stages = g_flush_mmas / per_stage > 0 ? g_flush_mmas / per_stage : 1;
   }
+  p.a_tmem = g_a_tmem;
   p.out_t = (__nv_bfloat16*)d->out_t; p.out_t_plane_stride = d->out_t_plane_stride; p.ld_t = d->ld_t;
   p.mask_src = (const __nv_bfloat16*)d->mask_src; p.mask_plane_stride = d->mask_plane_stride;
   p.mask_planes = d->mask_planes;

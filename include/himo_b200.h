@@ -154,6 +154,10 @@ int himo_conv2d_nhwc(const himo_conv_desc* desc, void* stream);
 int himo_conv_set_flush_iters(int mmas);
 /* A/B knob: 0 disables the haloed-row reuse of the activation tile across the kx taps (default on). */
 int himo_conv_set_halo(int enable);
+/* A/B knob: 1 stages the activation slices in tensor memory (tcgen05.cp.128x256b + TS-form MMAs: a_hi is read from
+ * shared memory once for its two products); default 0 = both operands from shared memory (SS form).  Bit-identical;
+ * measured neutral to slower on B200 (profiles/r01_conv_a_tmem_ab.txt). */
+int himo_conv_set_a_tmem(int enable);
 /* Tuning knob: CTA pairs (cta_group::2) are used for tiles with at least this many hi*hi MMAs (default 48). */
 int himo_conv_set_pair_min_mmas(int n);
 /* A/B knob: 0 disables the 256-channel-wide tiles (one N tile per CTA pair, accumulators fill TMEM) used for the
