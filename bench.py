@@ -324,8 +324,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "stages_ms": {"embedder": stage[0], "backbone": stage[1], "decoder": stage[2]},
-        "roofline": {"bound": "tensor", "kernel": "k_conv_umma (the 29 convolution launches of a step; the stage time "
-                                                   "also holds the 3 bilinear upsamples, 3 % of it)",
+        "roofline": {"bound": "tensor", "kernel": "k_conv_umma / k_conv_wide (the 29 convolution launches of a step; the stage "
+                                                   "time also holds the 3 bilinear upsamples, 3 % of it)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                      "traffic": traffic, "traffic_unit": "DRAM bytes per step over those launches (ncu, profiles/"
                                                          "r01_backbone_traffic.json); algorithmic = FLOPs, see DESIGN.md",
