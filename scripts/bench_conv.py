@@ -8,6 +8,8 @@ LAYERS = [  # name, H, W, Cin, Cout, ksize, stride, groups, act (1 = bias + GELU
     ("enc1.0 32->64 s2 @512 x3", 512, 512, 32, 64, 3, 2, 3, 1, 0),
     ("enc1.1 64->64 @256 x3", 256, 256, 64, 64, 3, 1, 3, 1, 0),
     ("enc2.1 128->128 @128 x3", 128, 128, 128, 128, 3, 1, 3, 1, 0),
+    ("enc2.1 no-act (epilogue probe)", 128, 128, 128, 128, 3, 1, 3, 0, 0),
+    ("enc2.1 no-act fp32 out (probe)", 128, 128, 128, 128, 3, 1, 3, 0, 1),
     ("enc3.1 256->256 @64 x3", 64, 64, 256, 256, 3, 1, 3, 1, 0),
     ("b1.u3 1x1 384->384 @128", 128, 128, 384, 384, 1, 1, 1, 0, 0),
     ("b1.u4 768->384 @128", 128, 128, 768, 384, 3, 1, 1, 0, 0),

@@ -165,3 +165,21 @@ def test_fused_decoder_matches_unfused_path():
         L.himo_deflowpp_set_fused_decoder(1)
     assert ref.shape == got.shape and ref.abs().max() > 0
     assert (ref - got).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("n0", [1, 127, 256, 257, 1000])
+def test_ragged_point_counts_against_oracle(n0, net0):
+    """Tile-boundary cases of the fused decoder (256-point CTA-pair tiles, padded rows) and of the embedder:
+    pc0 with 1 / 127 / 256 / 257 / 1000 points against dense neighbour frames, flow vs the CPU oracle."""
+    sd = weights.synth_deflowpp_state_dict(7)
+    net0.load_state_dict(sd)
+    tr = frames.lidar_triple(6000, 50 + n0)
+    tr = dict(tr)
+    tr["pc0"] = np.ascontiguousarray(tr["pc0"][:n0])
+    ref = deflowpp_ref.deflowpp_forward(sd, tr["pch1"], tr["pc0"], tr["pc1"], tr["poseh1"], tr["pose0"], tr["pose1"])
+    out = net0(_batch(tr))
+    assert (out["pc0_valid_point_idxes"][0].cpu() == ref["pc0_valid_point_idxes"]).all()
+    got = out["flow"][0].cpu()
+    assert got.shape == ref["flow"].shape
+    if got.numel():
+        assert (got - ref["flow"]).abs().max().item() <= FLOW_TOL

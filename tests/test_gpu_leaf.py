@@ -189,3 +189,35 @@ def test_chamfer_radius_matches_truncated_reference(kind, radius):
         exp_i = np.where(keep, ref_i, -1)
         assert (got_d.cpu().numpy() == exp_d).all() and (got_i.cpu().numpy() == exp_i).all()
     assert 0 < keep.sum()
+
+
+def test_chamfer_properties_million_points():
+    """BASELINE configs[4] size (1 M-point pair; 2^28-cell key space, 0.125 m finest cells): size-independent
+    properties -- valid indices, distances equal the recomputed squared distance to the reported neighbour, no sampled
+    candidate is closer, and the radius-limited search agrees with the full search inside the radius."""
+    n = 1_000_000
+    a, b = frames.uniform_frame(n, 71), frames.uniform_frame(n, 72)
+    a[: n // 2] *= 0.25        # a dense core inside a sparse shell: both start levels and the refinement are exercised
+    b[: n // 2] *= 0.25
+    d0, d1, i0, i1 = _chamfer_gpu(a, b)
+    assert i0.min() >= 0 and i0.max() < n and i1.min() >= 0 and i1.max() < n
+    dd = (b[i0] - a).astype(np.float64)
+    np.testing.assert_allclose(d0, (dd ** 2).sum(1), rtol=1e-5, atol=1e-9)
+    rng = np.random.default_rng(1)
+    sel = rng.integers(0, n, 200_000)
+    cand = rng.integers(0, n, (sel.size, 8))
+    dc = ((b[cand] - a[sel][:, None, :]).astype(np.float64) ** 2).sum(-1)
+    assert (dc.min(1) >= d0[sel].astype(np.float64) * (1 - 1e-5) - 1e-9).all()
+    # brute force on a sample of queries (exact check of the reported neighbour)
+    q = rng.integers(0, n, 64)
+    for k in q:
+        full = ((b - a[k]).astype(np.float32) ** 2)
+        ref = np.float32(full[:, 2] + (full[:, 1] + full[:, 0]))     # not the fma rounding: compare with tolerance
+        assert abs(float(ref.min()) - float(d0[k])) <= 1e-5 * max(1.0, float(ref.min()))
+    pa, pb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    r0 = torch.zeros(n, device="cuda"); r1 = torch.zeros(n, device="cuda")
+    j0 = torch.zeros(n, dtype=torch.int32, device="cuda"); j1 = torch.zeros(n, dtype=torch.int32, device="cuda")
+    chamfer3d_ext.forward_radius(pa, pb, r0, r1, j0, j1, 1.0)
+    keep = d0 <= np.float32(1.0)
+    assert (r0.cpu().numpy()[keep] == d0[keep]).all() and (j0.cpu().numpy()[keep] == i0[keep]).all()
+    assert (j0.cpu().numpy()[~keep] == -1).all()
