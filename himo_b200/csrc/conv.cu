@@ -926,6 +926,7 @@ static int g_enable_2cta = 1;
 static int g_weights_resident = 1;
 static int g_wide_tiles = 1;
 static int g_pair_min_mmas = 48;
+static int g_max_sms = kNumSMs;   // experiment knob: SMs a persistent launch may occupy
 static int g_a_tmem = 0;   // measured neutral on the 128-wide layers, slower on the 64-wide ones (profiles/r01_conv_a_tmem_ab.txt)
 
 template <int BN, int P, int NX, int CG, int WR = 0>
@@ -938,7 +939,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
     configured = true;
   }
   const int work = p.total_tiles / CG;
-  int grid = (work < kNumSMs / CG || !g_persistent) ? work : kNumSMs / CG;   // persistent: one CTA (pair) per SM (pair)
+  int grid = (work < g_max_sms / CG || !g_persistent) ? work : g_max_sms / CG;   // persistent: one CTA (pair) per SM (pair)
   grid *= CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = C::kTotal; cfg.stream = stream;
@@ -963,6 +964,9 @@ extern "C" int himo_conv_set_halo(int enable) { g_disable_halo = enable ? 0 : 1;
 extern "C" int himo_conv_set_2cta(int enable) { g_enable_2cta = enable ? 1 : 0; return HIMO_OK; }
 // A/B knob: 0 reads both MMA operands from shared memory (SS form) instead of staging A in tensor memory.
 extern "C" int himo_conv_set_a_tmem(int enable) { g_a_tmem = enable ? 1 : 0; return HIMO_OK; }
+// Experiment knob: number of SMs a persistent convolution launch occupies (default all 148); used to tell a per-SM
+// operand-fill limit from a chip-wide one.
+extern "C" int himo_conv_set_max_sms(int n) { g_max_sms = n < 2 ? 2 : (n > kNumSMs ? kNumSMs : n); return HIMO_OK; }
 // Tuning knob: CTA pairs are used when a tile carries at least this many hi*hi MMAs (default 48).
 extern "C" int himo_conv_set_pair_min_mmas(int n) { g_pair_min_mmas = n; return HIMO_OK; }
 // A/B knob: 0 disables the 256-wide N tiles (k_conv_wide) of the 256-channel encoder layers.

@@ -158,6 +158,8 @@ int himo_conv_set_halo(int enable);
  * shared memory once for its two products); default 0 = both operands from shared memory (SS form).  Bit-identical;
  * measured neutral to slower on B200 (profiles/r01_conv_a_tmem_ab.txt). */
 int himo_conv_set_a_tmem(int enable);
+/* Experiment knob: SMs a persistent convolution launch may occupy (default 148). */
+int himo_conv_set_max_sms(int n);
 /* Tuning knob: CTA pairs (cta_group::2) are used for tiles with at least this many hi*hi MMAs (default 48). */
 int himo_conv_set_pair_min_mmas(int n);
 /* A/B knob: 0 disables the 256-channel-wide tiles (one N tile per CTA pair, accumulators fill TMEM) used for the

@@ -30,6 +30,8 @@ if os.environ.get("CTA2") is not None:
     L.himo_conv_set_2cta(int(os.environ["CTA2"]))
 if os.environ.get("HALO") is not None:
     L.himo_conv_set_halo(int(os.environ["HALO"]))
+if os.environ.get("MAXSMS") is not None:
+    L.himo_conv_set_max_sms(int(os.environ["MAXSMS"]))
 if os.environ.get("ATMEM") is not None:
     L.himo_conv_set_a_tmem(int(os.environ["ATMEM"]))
 if os.environ.get("PAIRMIN") is not None:
