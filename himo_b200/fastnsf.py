@@ -177,8 +177,9 @@ class FastNSF:
         self.last_info = {k: out[k] for k in ("loss", "iterations")}
         return out
 
-    def forward(self, batch: Dict) -> Dict[str, List[torch.Tensor]]:
-        """fastnsf.py:180-222."""
+    def forward(self, batch: Dict, init_state_dicts: Optional[List[Dict]] = None) -> Dict[str, List[torch.Tensor]]:
+        """fastnsf.py:180-222.  `init_state_dicts` (one Neural_Prior state_dict per batch item) replaces the
+        per-frame seeded initial weights -- the reference draws them from the global torch RNG (fastnsf.py:110-113)."""
         flows, pose_flows = [], []
         for b in range(len(batch["pose0"])):
             pc0, pc1 = batch["pc0"][b], batch["pc1"][b]
@@ -190,7 +191,7 @@ class FastNSF:
                 T = cal_pose0to1(batch["pose0"][b], batch["pose1"][b])
             pf = rigid_flow(sel0.contiguous(), T)
             tr0 = sel0 + pf                                        # fastnsf.py:199 (warp), :201 (pose flow)
-            res = self.optimize(tr0, sel1)
+            res = self.optimize(tr0, sel1, init_state_dict=init_state_dicts[b] if init_state_dicts else None)
             final = torch.zeros_like(pc0)
             final[rm0] = res["flow"]
             flows.append(final)

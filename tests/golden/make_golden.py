@@ -10,9 +10,9 @@ What is pinned by what
   deflowpp_n*.npz          outputs of the reference's OWN `src.models.DeFlowPP` class (imported from
                            /root/reference through oracle/ref_shims.py) on seeded synthetic triples with
                            himo_b200.weights.synth_deflowpp_state_dict(seed) loaded strictly
-  neural_prior_*.npz       outputs / gradients of the reference's `Neural_Prior` + `EarlyStopping`
-                           trace (OSF/src/models/basic/nsfp_module.py)
-  himo_compdis_*.npz       HiMo `flow2compDis` / `ego_pts_mask` (utils/__init__.py:26-47) outputs
+  fastnsf_n*.npz           output of the reference's OWN `src.models.FastNSF` class (its Neural_Prior, EarlyStopping,
+                           Adam, grid_sample lookup) with the initial weights it drew, on a cropped synthetic pair;
+                           the FastGeodis call is served by the restated transform (parity unpinned for that piece)
 """
 from __future__ import annotations
 
@@ -62,12 +62,41 @@ def deflowpp(models, n, seed, kind):
         pch1_valid_point_idxes=out["pch1_valid_point_idxes"][0].numpy())
 
 
+def fastnsf(models, n, seed, itr_num, patience, half_extent):
+    """The reference's OWN `src.models.FastNSF` (fastnsf.py:83-222; FastGeodis replaced by the restated transform of
+    oracle/ref_shims.py -- the one unpinned piece) on a cropped synthetic pair.  The initial weights are whatever
+    `Neural_Prior()` + `init_weights()` draw from the global torch RNG after torch.manual_seed(seed) (fastnsf.py:110-113);
+    they are stored so that the oracle and the CUDA path can start from exactly the same network."""
+    import importlib
+    npm = importlib.import_module("src.models.basic.nsfp_module")
+    tr = frames.lidar_triple(n, seed)
+    crop = lambda a: np.ascontiguousarray(a[(np.abs(a[:, 0]) < half_extent) & (np.abs(a[:, 1]) < half_extent)])
+    pc0, pc1 = crop(tr["pc0"]), crop(tr["pc1"])
+    torch.set_num_threads(1)
+    torch.manual_seed(seed)
+    net = npm.Neural_Prior(filter_size=128, act_fn="relu", layer_size=8)
+    net.init_weights()
+    sd0 = {k: v.detach().clone().numpy() for k, v in net.state_dict().items()}
+    model = models.FastNSF(itr_num=itr_num, early_patience=patience)     # conf/model/fastnsf.yaml:13: patience 10
+    torch.manual_seed(seed)                                              # optimize() re-draws the same network
+    batch = {"pc0": [torch.from_numpy(pc0)], "pc1": [torch.from_numpy(pc1)],
+             "pose0": [torch.from_numpy(tr["pose0"])], "pose1": [torch.from_numpy(tr["pose1"])]}
+    out = model(batch)
+    np.savez_compressed(
+        os.path.join(HERE, f"fastnsf_n{pc0.shape[0]}_s{seed}_k{itr_num}.npz"),
+        pc0=pc0, pc1=pc1, pose0=tr["pose0"], pose1=tr["pose1"], itr_num=np.int64(itr_num), patience=np.int64(patience),
+        flow=out["flow"][0].detach().numpy(), pose_flow=out["pose_flow"][0].detach().numpy(),
+        **{"w::" + k: v for k, v in sd0.items()})
+
+
 def main():
     assert ref_shims.reference_available(), "needs /root/reference"
     fixture_clouds()
     models = ref_shims.import_models()
     deflowpp(models, 2000, 11, "lidar")
     deflowpp(models, 3000, 12, "uniform")
+    fastnsf(models, 12000, 13, 15, 10, 12.0)
+    fastnsf(models, 12000, 13, 3, 10, 12.0)     # short horizon: before the optimiser's chaotic divergence sets in
     for name in sorted(os.listdir(HERE)):
         if name.endswith(".npz"):
             print(name, os.path.getsize(os.path.join(HERE, name)))

@@ -10,7 +10,7 @@ import torch
 
 from conftest import GOLDEN
 from himo_b200 import weights
-from oracle import deflowpp_ref, ref_shims
+from oracle import deflowpp_ref, fastnsf_ref, ref_shims
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "deflowpp_*.npz"))))
@@ -41,3 +41,21 @@ def test_deflowpp_oracle_matches_live_reference():
     out = deflowpp_ref.deflowpp_forward(sd, tr["pch1"], tr["pc0"], tr["pc1"], tr["poseh1"], tr["pose0"], tr["pose1"])
     assert (ref["pc0_valid_point_idxes"][0] == out["pc0_valid_point_idxes"]).all()
     np.testing.assert_allclose(out["flow"].numpy(), ref["flow"][0].numpy(), rtol=0, atol=5e-5)
+
+
+def _golden_prior_state_dict(z):
+    return {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w::")}
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "fastnsf_*.npz"))))
+def test_fastnsf_oracle_matches_reference_golden(path):
+    """oracle/fastnsf_ref.py against the output of the reference's own `src.models.FastNSF` class
+    (OSF/src/models/fastnsf.py:83-222) started from the very weights that class drew; both sides use the restated
+    FastGeodis transform, so this pins everything of H3 except that transform."""
+    z = np.load(path)
+    torch.set_num_threads(1)
+    out = fastnsf_ref.fastnsf_forward(_golden_prior_state_dict(z), z["pc0"], z["pc1"], z["pose0"], z["pose1"],
+                                      itr_num=int(z["itr_num"]), patience=int(z["patience"]))
+    np.testing.assert_array_equal(out["pose_flow"].numpy(), z["pose_flow"])
+    assert out["iterations"] == int(z["itr_num"])
+    np.testing.assert_allclose(out["final_flow"].numpy(), z["flow"], rtol=0, atol=2e-6)
