@@ -933,7 +933,10 @@ template <int BN, int P, int NX, int CG, int WR = 0>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
   using C = ConvCfg<BN, P, NX, CG, WR>;
   auto kern = k_conv_umma<BN, P, NX, CG, WR>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};      // the attribute is per device: one flag per device ordinal
+  int dev_ = 0;
+  HIMO_CUDA_RET(cudaGetDevice(&dev_));
+  bool& configured = configured_dev[dev_ & 63];
   if (!configured) {
     HIMO_CUDA_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
     configured = true;
@@ -1091,7 +1094,10 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return HIMO_ERR_ARG;
     }
-    static bool wide_configured = false;
+    static bool wide_configured_dev[64] = {};
+    int dev_ = 0;
+    HIMO_CUDA_RET(cudaGetDevice(&dev_));
+    bool& wide_configured = wide_configured_dev[dev_ & 63];
     if (!wide_configured) {
       HIMO_CUDA_RET(cudaFuncSetAttribute(k_conv_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideTotal));
       wide_configured = true;

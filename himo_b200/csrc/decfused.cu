@@ -434,7 +434,10 @@ int dec_fused(const __nv_bfloat16* hx, int n, int n_pad, int num_iters, const hi
   p.s_q = w->gru_q_s != 0.f ? w->gru_q_s : 1.f;
   p.s_0 = w->dec0_s != 0.f ? w->dec0_s : 1.f;
   p.pt4 = pt4; p.flow = flow;
-  static bool configured = false;
+  static bool configured_dev[64] = {};      // the attribute is per device: one flag per device ordinal
+  int dev_ = 0;
+  HIMO_CUDA_RET(cudaGetDevice(&dev_));
+  bool& configured = configured_dev[dev_ & 63];
   if (!configured) {
     HIMO_CUDA_RET(cudaFuncSetAttribute(k_dec_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kDfTotal));
     configured = true;
