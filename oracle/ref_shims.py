@@ -133,3 +133,49 @@ def import_models():
     import io
     with contextlib.redirect_stdout(io.StringIO()):
         return importlib.import_module("src.models")
+
+
+def _av2_modules() -> None:
+    """`av2` and `rich` are imported at module level by OSF/src/utils/av2_eval.py (:19,:26,:77-80) but only their
+    category enum matters for the metric arithmetic; the enum is rebuilt from the table HiMo's scorer carries
+    (tools/test/score.py:29-60, identical order)."""
+    import enum
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("himo_ref_score_for_av2", os.path.join(REFERENCE_ROOT, "tools", "test", "score.py"))
+    score = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(score)
+    names = [k for k, v in sorted(score.CATEGORY_TO_INDEX.items(), key=lambda kv: kv[1]) if k != "NONE"]
+    cats = enum.Enum("AnnotationCategories", {n: n for n in names}, type=str)
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    if not hasattr(np, "NaN"):
+        np.NaN = np.nan          # eval_metric.py:143 predates NumPy 2.0
+    mod("av2"); mod("av2.datasets"); mod("av2.datasets.sensor")
+    mod("av2.datasets.sensor.constants", AnnotationCategories=cats)
+    mod("av2.geometry"); mod("av2.geometry.geometry"); mod("av2.geometry.se3", SE3=object)
+    mod("av2.utils"); mod("av2.utils.typing", NDArrayFloat=np.ndarray, NDArrayBool=np.ndarray, NDArrayInt=np.ndarray)
+    mod("av2.utils.io", read_feather=None)
+    mod("rich"); mod("rich.progress", track=lambda it, **_k: it)
+    for name in ("torch",):
+        pass
+    # av2_eval.py annotates with BoolTensor (torch) further down; provide it through typing if missing
+    import builtins
+    if not hasattr(builtins, "BoolTensor"):
+        builtins.BoolTensor = torch.BoolTensor
+
+
+def import_eval_metric():
+    """-> the reference `src.utils.eval_metric` module (evaluate_leaderboard*, evaluate_ssf, OfficialMetrics)."""
+    install()
+    _av2_modules()
+    import importlib
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        return importlib.import_module("src.utils.eval_metric")

@@ -13,6 +13,7 @@ What is pinned by what
   fastnsf_n*.npz           output of the reference's OWN `src.models.FastNSF` class (its Neural_Prior, EarlyStopping,
                            Adam, grid_sample lookup) with the initial weights it drew, on a cropped synthetic pair;
                            the FastGeodis call is served by the restated transform (parity unpinned for that piece)
+  av2_metrics_*.json       normalised OfficialMetrics of the reference's OWN OSF/src/utils/eval_metric.py on seeded frames
 """
 from __future__ import annotations
 
@@ -89,6 +90,19 @@ def fastnsf(models, n, seed, itr_num, patience, half_extent):
         **{"w::" + k: v for k, v in sd0.items()})
 
 
+def av2_metrics(seeds):
+    """Normalised `OfficialMetrics` state of the reference's OWN OSF/src/utils/eval_metric.py (three-way EPE, bucketed
+    normalised EPE, range-wise SSF EPE) over seeded synthetic frames (tests/test_av2_metrics.py::synth_frame)."""
+    import json
+    sys.path.insert(0, os.path.dirname(HERE))
+    import test_av2_metrics as T
+    ref = ref_shims.import_eval_metric()
+    summary = T._summary(T._run(ref, seeds))
+    name = "av2_metrics_s" + "_".join(str(s) for s in seeds) + ".json"
+    json.dump({"seeds": list(seeds), "generator": "tests/golden/make_golden.py::av2_metrics (reference eval_metric.py)",
+               "summary": summary}, open(os.path.join(HERE, name), "w"), indent=1)
+
+
 def main():
     assert ref_shims.reference_available(), "needs /root/reference"
     fixture_clouds()
@@ -97,6 +111,7 @@ def main():
     deflowpp(models, 3000, 12, "uniform")
     fastnsf(models, 12000, 13, 15, 10, 12.0)
     fastnsf(models, 12000, 13, 3, 10, 12.0)     # short horizon: before the optimiser's chaotic divergence sets in
+    av2_metrics([11, 12, 13])
     for name in sorted(os.listdir(HERE)):
         if name.endswith(".npz"):
             print(name, os.path.getsize(os.path.join(HERE, name)))
