@@ -68,3 +68,36 @@ def test_save_fastnsf_plumbing(data_dir):
     pf = himo.pose_flow_np(item["pc0"], item["pose0"], item["pose1"])
     # ground points carry the ego-motion flow only (OSF/src/runner.py:149-155)
     np.testing.assert_allclose(f[item["gm0"]], pf[item["gm0"]], rtol=0, atol=1e-4)
+
+
+def test_nnd_autolabel_matches_bruteforce(tmp_path):
+    """himo_b200.autolabel.run_nnd (OSF/process.py:106-172) on a synthetic two-scene store: the labels written under
+    `nnd` equal the reference rule applied to brute-force nearest-neighbour distances (oracle/leaf_ops.c)."""
+    import numpy as np
+    from himo_b200 import autolabel, store
+    from himo_b200.dataset import HDF5Dataset
+    from oracle import leaf
+    d = str(tmp_path / "ds")
+    st = store.write_synthetic_dataset(d, n_scenes=2, n_frames=4, n_points=3000, seed=5)
+    n = autolabel.run_nnd(d, min_nnd=0.14, store=st)
+    ds = HDF5Dataset(d, store=st)
+    assert n == len(ds.data_index) == 8
+    moving = 0
+    for scene_id, b in ds.scene_id_bounds.items():
+        norm = st.read(scene_id, ds.data_index[b["min_index"]][1], "pose")
+        for i in range(b["min_index"], b["max_index"] + 1):
+            ts = ds.data_index[i][1]
+            j = i - 1 if i == b["max_index"] else i + 1
+            ts1 = ds.data_index[j][1]
+            pc0 = st.read(scene_id, ts, "lidar")[:, :3]
+            pose0 = np.linalg.inv(norm) @ st.read(scene_id, ts, "pose")
+            pose1 = np.linalg.inv(norm) @ st.read(scene_id, ts1, "pose")
+            ego = np.linalg.inv(pose1) @ pose0
+            tr0 = (pc0 @ ego[:3, :3].T + ego[:3, 3]).astype(np.float32)
+            pc1 = np.ascontiguousarray(st.read(scene_id, ts1, "lidar")[:, :3]).astype(np.float32)
+            d0 = leaf.nn_bruteforce(np.ascontiguousarray(tr0), pc1)[0]
+            ref = ((d0 >= pow(0.14, 2)) & (d0 < pow(4.4, 2))).astype(np.uint8)      # process.py:124
+            got = st.read(scene_id, ts, "nnd")
+            assert got.dtype == np.uint8 and (got == ref).all()
+            moving += int(ref.sum())
+    assert moving > 0
