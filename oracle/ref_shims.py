@@ -135,6 +135,14 @@ def import_models():
         return importlib.import_module("src.models")
 
 
+def import_lossfuncs():
+    """-> the reference `src.lossfuncs.selfsupervise` module (seflowLoss, seflowppLoss) over the chamfer3D shim."""
+    install()
+    _av2_modules()          # src/lossfuncs/__init__.py pulls in supervise.py -> av2_eval.py
+    import importlib
+    return importlib.import_module("src.lossfuncs.selfsupervise")
+
+
 def _av2_modules() -> None:
     """`av2` and `rich` are imported at module level by OSF/src/utils/av2_eval.py (:19,:26,:77-80) but only their
     category enum matters for the metric arithmetic; the enum is rebuilt from the table HiMo's scorer carries

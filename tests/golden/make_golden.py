@@ -13,6 +13,8 @@ What is pinned by what
   fastnsf_n*.npz           output of the reference's OWN `src.models.FastNSF` class (its Neural_Prior, EarlyStopping,
                            Adam, grid_sample lookup) with the initial weights it drew, on a cropped synthetic pair;
                            the FastGeodis call is served by the restated transform (parity unpinned for that piece)
+  nsfp_n*.npz              output of the reference's OWN `src.models.NSFP` class with the network it drew, on a cropped synthetic pair
+  seflow_loss_*.npz        loss terms + flow gradient of the reference's OWN OSF/src/lossfuncs/selfsupervise.py on seeded frames
   av2_metrics_*.json       normalised OfficialMetrics of the reference's OWN OSF/src/utils/eval_metric.py on seeded frames
 """
 from __future__ import annotations
@@ -90,6 +92,29 @@ def fastnsf(models, n, seed, itr_num, patience, half_extent):
         **{"w::" + k: v for k, v in sd0.items()})
 
 
+def nsfp(models, n, seed, itr_num, patience, half_extent):
+    """The reference's OWN `src.models.NSFP` (nsfp.py:28-186, chamfer3D served by the brute-force shim) on a cropped
+    synthetic pair; the default-initialised network it draws after torch.manual_seed(seed) is stored alongside."""
+    import importlib
+    npm = importlib.import_module("src.models.basic.nsfp_module")
+    tr = frames.lidar_triple(n, seed)
+    crop = lambda a: np.ascontiguousarray(a[(np.abs(a[:, 0]) < half_extent) & (np.abs(a[:, 1]) < half_extent)])
+    pc0, pc1 = crop(tr["pc0"]), crop(tr["pc1"])
+    torch.set_num_threads(1)
+    torch.manual_seed(seed)
+    sd0 = {k: v.detach().clone().numpy() for k, v in npm.Neural_Prior(filter_size=128, act_fn="relu", layer_size=8).state_dict().items()}
+    model = models.NSFP(itr_num=itr_num, early_patience=patience)
+    torch.manual_seed(seed)
+    batch = {"pc0": [torch.from_numpy(pc0)], "pc1": [torch.from_numpy(pc1)],
+             "pose0": [torch.from_numpy(tr["pose0"])], "pose1": [torch.from_numpy(tr["pose1"])]}
+    out = model(batch)
+    np.savez_compressed(
+        os.path.join(HERE, f"nsfp_n{pc0.shape[0]}_s{seed}_k{itr_num}.npz"),
+        pc0=pc0, pc1=pc1, pose0=tr["pose0"], pose1=tr["pose1"], itr_num=np.int64(itr_num), patience=np.int64(patience),
+        flow=out["flow"][0].detach().numpy(), pose_flow=out["pose_flow"][0].detach().numpy(),
+        **{"w::" + k: v for k, v in sd0.items()})
+
+
 def av2_metrics(seeds):
     """Normalised `OfficialMetrics` state of the reference's OWN OSF/src/utils/eval_metric.py (three-way EPE, bucketed
     normalised EPE, range-wise SSF EPE) over seeded synthetic frames (tests/test_av2_metrics.py::synth_frame)."""
@@ -103,6 +128,23 @@ def av2_metrics(seeds):
                "summary": summary}, open(os.path.join(HERE, name), "w"), indent=1)
 
 
+def seflow_losses(cases):
+    """Terms and d(sum of terms)/d(est_flow) of the reference's OWN seflowLoss / seflowppLoss
+    (OSF/src/lossfuncs/selfsupervise.py:25-190, chamfer3D served by the brute-force shim) on the seeded clustered
+    frames of tests/test_lossfuncs.py::synth_loss_frame."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import test_lossfuncs as T
+    ref = ref_shims.import_lossfuncs()
+    for seed, n, frac in cases:
+        frame = T.synth_loss_frame(seed, n, dynamic_fraction=frac)
+        out = {"seed": np.int64(seed), "n": np.int64(n), "frac": np.float64(frac)}
+        for name in ("seflowLoss", "seflowppLoss"):
+            v, g = T.run_loss(getattr(ref, name), frame)
+            out[name + "_terms"] = np.array([v[k] for k in T.TERMS], np.float64)
+            out[name + "_grad"] = g.astype(np.float32)
+        np.savez_compressed(os.path.join(HERE, f"seflow_loss_s{seed}_n{n}.npz"), **out)
+
+
 def main():
     assert ref_shims.reference_available(), "needs /root/reference"
     fixture_clouds()
@@ -111,7 +153,10 @@ def main():
     deflowpp(models, 3000, 12, "uniform")
     fastnsf(models, 12000, 13, 15, 10, 12.0)
     fastnsf(models, 12000, 13, 3, 10, 12.0)     # short horizon: before the optimiser's chaotic divergence sets in
+    nsfp(models, 6000, 14, 3, 30, 12.0)
+    nsfp(models, 6000, 14, 12, 30, 12.0)
     av2_metrics([11, 12, 13])
+    seflow_losses([(31, 2400, 0.35), (33, 900, 0.5)])
     for name in sorted(os.listdir(HERE)):
         if name.endswith(".npz"):
             print(name, os.path.getsize(os.path.join(HERE, name)))
