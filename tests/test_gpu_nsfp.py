@@ -38,11 +38,16 @@ def test_nsfp_forward_matches_reference_golden(k, atol):
 
 
 def test_nsfp_loss_decreases_and_early_stop():
+    """On this pair the first Adam steps overshoot: with patience 5 the run ends after 1 + 5 iterations holding the
+    initial flow; with the default patience the loss gets below where it started (0.1527 -> 0.1465 after 45)."""
     (path,) = glob.glob(os.path.join(GOLDEN, "nsfp_*_k3.npz"))
     z = np.load(path)
     short = nsfp.NSFP(itr_num=1)
     short(_batch(z), init_state_dicts=[golden_state_dict(z)])
-    longer = nsfp.NSFP(itr_num=60, early_patience=5)
+    assert short.last_info["loss"] == pytest.approx(0.152696, rel=1e-4)
+    impatient = nsfp.NSFP(itr_num=60, early_patience=5)
+    impatient(_batch(z), init_state_dicts=[golden_state_dict(z)])
+    assert impatient.last_info["iterations"] == 6 and impatient.last_info["loss"] == short.last_info["loss"]
+    longer = nsfp.NSFP(itr_num=45, early_patience=30)
     longer(_batch(z), init_state_dicts=[golden_state_dict(z)])
-    assert longer.last_info["loss"] < short.last_info["loss"]
-    assert 1 < longer.last_info["iterations"] <= 60
+    assert longer.last_info["iterations"] > 6 and longer.last_info["loss"] < 0.1515
