@@ -209,3 +209,16 @@ class FastNSFEngine:
         final = rigid_flow(pc0_all, T)                          # pose flow for every point
         final[~gm0] = final[~gm0] + res["flow"][0]              # runner.py:149-155
         return final.cpu().numpy()
+
+
+class NSFPEngine(FastNSFEngine):
+    """Same step for NSFP (conf/model/nsfp.yaml): only the per-pair optimiser differs (himo_b200/nsfp.py)."""
+
+    def __init__(self, device="cuda:0", seed: int = 0, **model_kw):
+        from . import _lib
+        from .nsfp import NSFP
+        _lib.lib()                                              # fail now, not at the first frame, if the library is missing
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        torch.manual_seed(seed)                                 # the networks are drawn from the global CPU RNG
+        self.net = NSFP(**model_kw)

@@ -65,6 +65,13 @@ def _build_engine(cfg: Dict[str, str], device):
                 kw[k] = cast(cfg[k])
         kw.setdefault("early_patience", 10)          # conf/model/fastnsf.yaml:13
         return FastNSFEngine(device=device, precision=cfg.get("precision", "fp32"), **kw), 2
+    if model == "nsfp":
+        from .engine import NSFPEngine
+        kw = {}
+        for k, cast in (("itr_num", int), ("early_patience", int), ("lr", float), ("min_delta", float)):
+            if k in cfg:
+                kw[k] = cast(cfg[k])
+        return NSFPEngine(device=device, **kw), 2              # conf/model/nsfp.yaml: patience 30
     from .engine import SeFlowPPEngine
     if ckpt.startswith("synthetic"):
         seed = int(ckpt.split(":")[1]) if ":" in ckpt else 0

@@ -70,6 +70,18 @@ def test_save_fastnsf_plumbing(data_dir):
     np.testing.assert_allclose(f[item["gm0"]], pf[item["gm0"]], rtol=0, atol=1e-4)
 
 
+def test_save_nsfp_plumbing(data_dir):
+    """NSFP through the save.py command line (few iterations: plumbing)."""
+    _run(["save.py", "model=nsfp", f"dataset_path={data_dir}", "itr_num=4", "res_name=nsfp"])
+    ds = HDF5Dataset(data_dir, vis_name="nsfp")
+    item = ds[1]
+    f = item["nsfp"]
+    assert f.shape == item["pc0"].shape and np.isfinite(f).all()
+    pf = himo.pose_flow_np(item["pc0"], item["pose0"], item["pose1"])
+    np.testing.assert_allclose(f[item["gm0"]], pf[item["gm0"]], rtol=0, atol=1e-4)
+    assert np.abs(f[~item["gm0"]] - pf[~item["gm0"]]).max() > 1e-4       # the optimised flow was added
+
+
 def test_nnd_autolabel_matches_bruteforce(tmp_path):
     """himo_b200.autolabel.run_nnd (OSF/process.py:106-172) on a synthetic two-scene store: the labels written under
     `nnd` equal the reference rule applied to brute-force nearest-neighbour distances (oracle/leaf_ops.c)."""
