@@ -178,6 +178,78 @@ def run_eval(cfg: Dict[str, str]):
     return None
 
 
+class _StoredFlow:
+    def __init__(self, name: str):
+        self.name = name
+
+    def infer(self, item):
+        if self.name not in item:
+            raise SystemExit(f"frame {item['scene_id']}/{item['timestamp']} holds no '{self.name}'")
+        return item[self.name]
+
+
+def run_validate(cfg: Dict[str, str], engine=None, n_frames: Optional[int] = None):
+    """OSF `python eval.py checkpoint=... dataset_path=... [data_mode=val]` (OSF/eval.py:27-72): run the model over the
+    eval index and score it with the AV2 / OpenSceneFlow metrics (ModelWrapper.eval_only_step_, OSF/src/trainer.py:
+    251-278; on_validation_epoch_end :226-249).  Frames of the eval index are dealt round-robin over the ranks; the
+    un-normalised `OfficialMetrics` are gathered on rank 0 and merged.  `engine` is injectable for the host tests."""
+    from . import av2_metrics as M, himo
+    from .dataset import HDF5Dataset
+    rank, world, local = _dist_env()
+    data_dir = cfg.get("dataset_path") or cfg.get("data_dir")
+    if not data_dir:
+        raise SystemExit("dataset_path=<dir with index_eval.pkl and scene files> is required")
+    stored = cfg.get("res_name", "") if cfg.get("model") == "stored" else ""
+    if cfg.get("model") == "stored":
+        # score flows a previous save.py run left in the store (no model, no GPU): `model=stored res_name=<name>`
+        if not stored:
+            raise SystemExit("model=stored needs res_name=<dataset name written by save.py>")
+        engine, n_frames = _StoredFlow(stored), 2
+    elif engine is None:
+        if not torch.cuda.is_available():
+            raise SystemExit("himo_b200 needs a CUDA device (no CPU fallback)")
+        dev = torch.device("cuda", local)
+        torch.cuda.set_device(dev)
+        engine, n_frames = _build_engine(cfg, dev)
+    ds = HDF5Dataset(data_dir, n_frames=n_frames or 2, eval=True, vis_name=stored)
+    metrics = M.OfficialMetrics()
+    t0, done = time.time(), 0
+    for i in range(rank, len(ds), world):
+        item = ds[i]
+        final = np.asarray(engine.infer(item), np.float32)
+        pc0 = np.asarray(item["pc0"], np.float32)[:, :3]
+        pose_flow = himo.pose_flow_np(pc0, item["pose0"], item["pose1"]).astype(np.float32)
+        m = np.asarray(item["eval_mask"], bool).squeeze()
+        gt, valid, cats = item["flow"], item["flow_is_valid"], item["flow_category_indices"]
+        metrics.step(M.evaluate_leaderboard(final[m], pose_flow[m], pc0[m], gt[m], valid[m], cats[m]),
+                     M.evaluate_leaderboard_v2(final[m], pose_flow[m], pc0[m], gt[m], valid[m], cats[m]),
+                     M.evaluate_ssf(final, pose_flow, pc0, gt, valid, cats))
+        done += 1
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(metrics, gathered, dst=0)
+        if rank == 0:
+            for other in gathered[1:]:
+                metrics.merge(other)
+        dist.barrier()
+    if rank != 0:
+        return None
+    metrics.normalize()
+    print(f"[eval] {done} frames on rank 0 of {world} in {time.time() - t0:.1f}s")
+    metrics.print(ssf_metrics=cfg.get("ssf_metrics", "false").lower() in ("1", "true", "yes"))
+    out = cfg.get("out_json")
+    if out:
+        import json
+        clean = lambda v: None if isinstance(v, float) and np.isnan(v) else v
+        json.dump({"epe_3way": {k: clean(float(v)) for k, v in metrics.epe_3way.items()},
+                   "bucketed": {k: {t: clean(float(v[t])) for t in ("Static", "Dynamic")} for k, v in metrics.bucketed.items()}},
+                  open(out, "w"), indent=1)
+    return metrics
+
+
 def main_save(argv=None):
     run_save(parse_overrides(sys.argv[1:] if argv is None else argv))
 
@@ -187,4 +259,9 @@ def main_save_zip(argv=None):
 
 
 def main_eval(argv=None):
-    run_eval(parse_overrides(sys.argv[1:] if argv is None else argv, aliases={"flow_mode": "res_name"}))
+    """HiMo's eval.py (`--data_dir/--res_name/--comp_dis_zip`: compensation-distance metrics) and, when a model is named
+    the hydra way (`checkpoint=` / `model=`), OpenSceneFlow's eval.py (scene-flow metrics of a fresh model run)."""
+    cfg = parse_overrides(sys.argv[1:] if argv is None else argv, aliases={"flow_mode": "res_name"})
+    if "checkpoint" in cfg or "model" in cfg:
+        return run_validate(cfg)
+    return run_eval(cfg)

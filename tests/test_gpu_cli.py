@@ -82,6 +82,20 @@ def test_save_nsfp_plumbing(data_dir):
     assert np.abs(f[~item["gm0"]] - pf[~item["gm0"]]).max() > 1e-4       # the optimised flow was added
 
 
+def test_validate_cli_matches_stored_flows(data_dir, tmp_path):
+    """OSF eval.py work-alike: `eval.py checkpoint=... dataset_path=...` runs the model over the eval index and prints
+    the AV2 metrics; the same metrics come out of scoring the flows save.py stored for the same checkpoint."""
+    _run(["save.py", "checkpoint=synthetic:4", f"dataset_path={data_dir}", "res_name=seflowpp_val"])
+    j1, j2 = str(tmp_path / "val.json"), str(tmp_path / "stored.json")
+    out = _run(["eval.py", "checkpoint=synthetic:4", f"dataset_path={data_dir}", f"out_json={j1}"])
+    assert "Three-way" in out
+    _run(["eval.py", "model=stored", "res_name=seflowpp_val", f"dataset_path={data_dir}", f"out_json={j2}"])
+    got, ref = json.load(open(j1)), json.load(open(j2))
+    for k in ("EPE_FD", "EPE_BS", "EPE_FS", "IoU", "Three-way"):
+        assert np.isfinite(got["epe_3way"][k])
+        assert got["epe_3way"][k] == pytest.approx(ref["epe_3way"][k], abs=2e-5)
+
+
 def test_nnd_autolabel_matches_bruteforce(tmp_path):
     """himo_b200.autolabel.run_nnd (OSF/process.py:106-172) on a synthetic two-scene store: the labels written under
     `nnd` equal the reference rule applied to brute-force nearest-neighbour distances (oracle/leaf_ops.c)."""

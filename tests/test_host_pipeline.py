@@ -131,3 +131,45 @@ def test_eval_two_ranks_matches_one(dataset_dir, tmp_path):
     for c in a:
         assert a[c]["overall"]["num_pts"] == b[c]["overall"]["num_pts"]
         assert abs(a[c]["overall"]["mpe"] - b[c]["overall"]["mpe"]) < 1e-9
+
+
+class _NoisyGtEngine:
+    """Stand-in model for the host tests of the validation driver: ground truth plus seeded per-frame noise."""
+
+    def infer(self, item):
+        rng = np.random.default_rng(int(item["timestamp"]) % (2 ** 31))
+        return (item["flow"] + rng.normal(0, 0.03, item["flow"].shape)).astype(np.float32)
+
+
+def _validate_worker(rank, world, port, data_dir, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = runner.run_validate({"dataset_path": data_dir, "out_json": out}, engine=_NoisyGtEngine())
+    dist.destroy_process_group()
+    assert (res is not None) == (rank == 0)
+
+
+def test_validate_driver_and_two_rank_merge(dataset_dir, tmp_path):
+    """OSF eval.py work-alike (runner.run_validate): per-frame AV2 metrics of a model run over the eval index; the
+    world_size-2 gloo run merges to the single-process result; a perfect model scores zero."""
+    import json
+    import torch.multiprocessing as mp
+    from himo_b200 import av2_metrics as M
+    one = runner.run_validate({"dataset_path": dataset_dir, "out_json": str(tmp_path / "v1.json")}, engine=_NoisyGtEngine())
+    assert isinstance(one, M.OfficialMetrics) and one.norm_flag
+    assert 0 < one.epe_3way["Three-way"] < 0.1
+    mp.spawn(_validate_worker, args=(2, 29617, dataset_dir, str(tmp_path / "v2.json")), nprocs=2, join=True)
+    a, b = json.load(open(tmp_path / "v1.json")), json.load(open(tmp_path / "v2.json"))
+    for k in ("EPE_FD", "EPE_BS", "EPE_FS", "IoU", "Three-way"):       # per-frame means: order-independent up to rounding
+        assert a["epe_3way"][k] == pytest.approx(b["epe_3way"][k], rel=1e-9, abs=1e-12)
+    for k, v in a["bucketed"].items():
+        for t in ("Static", "Dynamic"):
+            assert (v[t] is None and b["bucketed"][k][t] is None) or v[t] == pytest.approx(b["bucketed"][k][t], rel=1e-9, abs=1e-12)
+
+    # `model=stored res_name=flow`: score what is already in the store (here the ground truth itself) without a model
+    p = runner.run_validate({"dataset_path": dataset_dir, "model": "stored", "res_name": "flow"})
+    assert p.epe_3way["Three-way"] == pytest.approx(0.0, abs=1e-9) and p.epe_3way["IoU"] == pytest.approx(1.0)
+    with pytest.raises(SystemExit):
+        runner.run_validate({"dataset_path": dataset_dir, "model": "stored", "res_name": "not_there"})
