@@ -212,6 +212,16 @@ def run_validate(cfg: Dict[str, str], engine=None, n_frames: Optional[int] = Non
         torch.cuda.set_device(dev)
         engine, n_frames = _build_engine(cfg, dev)
     ds = HDF5Dataset(data_dir, n_frames=n_frames or 2, eval=True, vis_name=stored)
+    truthy = lambda v: str(v).lower() in ("1", "true", "yes")
+    data_mode = cfg.get("data_mode", "val")
+    if data_mode not in ("val", "test"):
+        raise SystemExit(f"data_mode={data_mode}: val or test")
+    version = int(cfg.get("leaderboard_version", 1))
+    if version not in (1, 2):
+        raise ValueError(f"Leaderboard version {version} is not valid. Please set it to 1 or 2.")     # OSF/eval.py:29-30
+    save_res = data_mode == "test" or truthy(cfg.get("save_res", "false"))         # trainer.py:281
+    res_dir = cfg.get("save_res_path") or os.path.join(os.path.dirname(os.path.abspath(data_dir)), "results",
+                                                       cfg.get("output", f"{cfg.get('model', 'deflowpp')}-{data_mode}-v{version}"))
     metrics = M.OfficialMetrics()
     t0, done = time.time(), 0
     for i in range(rank, len(ds), world):
@@ -220,10 +230,15 @@ def run_validate(cfg: Dict[str, str], engine=None, n_frames: Optional[int] = Non
         pc0 = np.asarray(item["pc0"], np.float32)[:, :3]
         pose_flow = himo.pose_flow_np(pc0, item["pose0"], item["pose1"]).astype(np.float32)
         m = np.asarray(item["eval_mask"], bool).squeeze()
-        gt, valid, cats = item["flow"], item["flow_is_valid"], item["flow_category_indices"]
-        metrics.step(M.evaluate_leaderboard(final[m], pose_flow[m], pc0[m], gt[m], valid[m], cats[m]),
-                     M.evaluate_leaderboard_v2(final[m], pose_flow[m], pc0[m], gt[m], valid[m], cats[m]),
-                     M.evaluate_ssf(final, pose_flow, pc0, gt, valid, cats))
+        if data_mode == "val":                  # only val carries ground truth (trainer.py:269)
+            gt, valid, cats = item["flow"], item["flow_is_valid"], item["flow_category_indices"]
+            metrics.step(M.evaluate_leaderboard(final[m], pose_flow[m], pc0[m], gt[m], valid[m], cats[m]),
+                         M.evaluate_leaderboard_v2(final[m], pose_flow[m], pc0[m], gt[m], valid[m], cats[m]),
+                         M.evaluate_ssf(final, pose_flow, pc0, gt, valid, cats))
+        if save_res:
+            from . import av2_submit
+            flow_out, is_dyn = av2_submit.leaderboard_arrays(final, pose_flow, m, version)
+            av2_submit.write_output_file(flow_out, is_dyn, (item["scene_id"], item["timestamp"]), res_dir, version)
         done += 1
     if world > 1:
         import torch.distributed as dist
@@ -237,8 +252,14 @@ def run_validate(cfg: Dict[str, str], engine=None, n_frames: Optional[int] = Non
         dist.barrier()
     if rank != 0:
         return None
-    metrics.normalize()
     print(f"[eval] {done} frames on rank 0 of {world} in {time.time() - t0:.1f}s")
+    if data_mode == "test":                     # trainer.py:213-224: zip for the online leaderboard, no metrics
+        from . import av2_submit
+        path = av2_submit.zip_res(res_dir, output_file=res_dir.rstrip("/") + ".zip", leaderboard_version=version,
+                                  is_supervised=truthy(cfg.get("supervised_flag", "true")))
+        print(f"Test results saved in: {res_dir}, zipped into {path}")
+        return path
+    metrics.normalize()
     metrics.print(ssf_metrics=cfg.get("ssf_metrics", "false").lower() in ("1", "true", "yes"))
     out = cfg.get("out_json")
     if out:
