@@ -77,6 +77,44 @@ def run_nnd(data_dir: str, scene_range: Sequence[int] = (-1, -1), overwrite: boo
     return written
 
 
+def shift_cluster_id(cluster: np.ndarray) -> np.ndarray:
+    """OSF/src/autolabel.py:18-29: 0 background, 1 reserved for "dynamic but unclustered", ids >= 1 move up by one."""
+    cluster = np.asarray(cluster)
+    return np.where(cluster > 0, cluster + 1, 0).astype(cluster.dtype)
+
+
+def seflow_auto(input_data) -> np.ndarray:
+    """OSF/src/autolabel.py:32-36 (HiMo Fig. 6 top): DUFOMap dynamic points keep their (shifted) cluster id."""
+    dufo = np.asarray(input_data["dufo"][:]).astype(np.uint8)
+    cluster = shift_cluster_id(np.asarray(input_data["dufocluster"][:]).astype(np.int16))
+    cluster[dufo == 0] = 0
+    return cluster
+
+
+def seflowpp_auto(input_data, tau1: float = 0.05, tau2: float = 0.30) -> np.ndarray:
+    """OSF/src/autolabel.py:39-62 (HiMo Eq. 5, Fig. 6 bottom): a cluster is dynamic when the fractions of its points
+    flagged by DUFOMap and by `nnd` satisfy min > tau1 and max > tau2; its points then carry the cluster id, all others
+    0.  Same result as the reference's loop over cluster ids, computed with three bincounts.  The output keeps the
+    reference's dtype (that of `dufo`, uint8: ids wrap modulo 256 there too)."""
+    dufo = np.asarray(input_data["dufo"][:]).astype(np.uint8)
+    cluster = shift_cluster_id(np.asarray(input_data["cluster"][:]).astype(np.int16))
+    nnd = np.asarray(input_data["nnd"][:]).astype(np.uint8)
+    dynamic = np.zeros_like(dufo)
+    if cluster.size == 0:
+        return dynamic
+    ids = np.where(cluster > 1, cluster, 0).astype(np.int64)            # 0 and 1 never qualify
+    k = int(ids.max()) + 1
+    total = np.bincount(ids, minlength=k)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r_dufo = np.bincount(ids, weights=dufo > 0, minlength=k) / total
+        r_nnd = np.bincount(ids, weights=nnd > 0, minlength=k) / total
+    keep = (np.minimum(r_dufo, r_nnd) > tau1) & (np.maximum(r_dufo, r_nnd) > tau2)
+    keep[0] = False
+    sel = keep[ids]
+    dynamic[sel] = cluster[sel]                                          # numpy casts int16 -> uint8 like the reference
+    return dynamic
+
+
 def main(argv=None):
     """`python -m himo_b200.autolabel --data_dir DIR [--scene_range 0,10] [--overwrite false] [--min_nnd 0.14]`:
     the fire entry the reference keeps commented at process.py:321.  Under torchrun the scenes of the range are dealt

@@ -52,3 +52,40 @@ def test_run_nnd_bookkeeping(tmp_path, monkeypatch):
     autolabel.run_nnd(d, scene_range=[0, 1], store=st, device="cpu", min_nnd=0.32)
     after = st.read(scenes[0], ds.data_index[0][1], "nnd")
     assert (after <= before).all() and after.sum() < before.sum()
+
+
+def _label_frame(seed, n=4000, n_clusters=40):
+    rng = np.random.default_rng(seed)
+    cluster = rng.integers(-1, n_clusters, n).astype(np.int16)       # <= 0: no cluster
+    p_dufo, p_nnd = rng.random(n_clusters + 1), rng.random(n_clusters + 1) * 0.6
+    c = np.clip(cluster, 0, None)
+    return {"dufo": (rng.random(n) < p_dufo[c]).astype(np.uint8), "nnd": (rng.random(n) < p_nnd[c]).astype(np.uint8),
+            "cluster": cluster, "dufocluster": cluster}
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_label_strategies_match_reference(seed):
+    """seflow_auto / seflowpp_auto (OSF/src/autolabel.py:32-62) against the reference's own functions, plus hand cases."""
+    fr = _label_frame(seed)
+    ours = autolabel.seflowpp_auto(fr)
+    assert ours.dtype == np.uint8 and set(np.unique(ours)) - {0} and (ours[fr["cluster"] <= 0] == 0).all()
+    from oracle import ref_shims
+    if ref_shims.reference_available():
+        import importlib
+        ref_shims.install()
+        ref = importlib.import_module("src.autolabel")
+        for kw in ({}, {"tau1": 0.01, "tau2": 0.05}, {"tau1": 0.4, "tau2": 0.9}):
+            np.testing.assert_array_equal(autolabel.seflowpp_auto(fr, **kw), ref.seflowpp_auto(fr, **kw))
+        np.testing.assert_array_equal(autolabel.seflow_auto(fr), ref.seflow_auto(fr))
+        np.testing.assert_array_equal(autolabel.shift_cluster_id(fr["cluster"]), ref.shiftClusterid(fr["cluster"]))
+
+
+def test_label_strategy_hand_case():
+    # cluster ids 1..3 -> shifted 2..4.  id 2: dufo 2/4, nnd 1/4 -> dynamic; id 3: nnd 0 -> min fails; id 4: both 1/10 -> max fails
+    cluster = np.array([1] * 4 + [2] * 4 + [3] * 10 + [0, -1], np.int16)
+    dufo = np.array([1, 1, 0, 0] + [1, 1, 1, 1] + [1] + [0] * 9 + [1, 1], np.uint8)
+    nnd = np.array([1, 0, 0, 0] + [0, 0, 0, 0] + [0, 1] + [0] * 8 + [1, 1], np.uint8)
+    out = autolabel.seflowpp_auto({"dufo": dufo, "nnd": nnd, "cluster": cluster})
+    assert out.tolist() == [2] * 4 + [0] * 4 + [0] * 10 + [0, 0]
+    assert autolabel.seflow_auto({"dufo": dufo, "dufocluster": cluster}).tolist() == [2, 2, 0, 0, 3, 3, 3, 3, 4] + [0] * 9 + [0, 0]
+    assert autolabel.seflowpp_auto({"dufo": dufo[:0], "nnd": nnd[:0], "cluster": cluster[:0]}).shape == (0,)
