@@ -2,7 +2,15 @@
 oracle/_ref/{chamfer3D,mmcv}.so by oracle/build_ref.py (the build container does that; the .so files travel with the
 snapshot).  Same inputs, same pybind signatures on both sides.  This is the pin the CPU restatement cannot give:
 voxel indices, scatter maps, nearest-neighbour indices and squared distances are required to be bit-equal to what the
-reference computes on the same GPU.  Skipped when the reference build is not present."""
+reference computes on the same GPU.  Skipped when the reference build is not present.
+
+Measured on a B200 (profiles/r01_ref_kernels_vs_ours.json, profiles/r01_ref_kernels_tests.log): voxel coordinates,
+scatter maps / counts / voxel order and ALL nearest-neighbour indices (376 k queries) are bit-equal; voxel means differ
+by 2.4e-7 (atomics order); the squared distances differ in the last bit for a share of the points because nvcc
+contracts the reference's `dx*dx + dy*dy + dz*dz` into fma(dz,dz, fma(dx,dx, dy*dy)) (SASS of oracle/_ref/chamfer3D.so)
+while our kernel and oracle/leaf_ops.c round every product.  The Chamfer test below states exactly that (indices
+equal, distances within two ulp); it was rewritten after that measurement and stays opt-in
+(HIMO_TEST_REF_KERNELS=1) until it has run once more on a B200.  The voxelize / scatter test passed as written."""
 import os
 
 import numpy as np
@@ -12,9 +20,9 @@ import torch
 from himo_b200 import chamfer3d_ext, frames, mmcv_ext
 from oracle import build_ref
 
+opt_in = pytest.mark.skipif(os.environ.get("HIMO_TEST_REF_KERNELS", "0") != "1",
+                            reason="opt-in until verified on a B200: HIMO_TEST_REF_KERNELS=1")
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("HIMO_TEST_REF_KERNELS", "0") != "1",
-                                 reason="opt-in until verified on a B200: HIMO_TEST_REF_KERNELS=1"),
               pytest.mark.skipif(not (build_ref.built("chamfer3D") and build_ref.built("mmcv")),
                                  reason="oracle/_ref/*.so not built (python -m oracle.build_ref)")]
 VS, RNG = frames.VOXEL_SIZE, frames.POINT_CLOUD_RANGE
@@ -46,13 +54,16 @@ def _chamfer(mod, a, b):
     return d0, d1, i0, i1
 
 
+@opt_in
 @pytest.mark.parametrize("kind,n,seed", [("fixture", 0, 0), ("lidar", 30000, 61), ("uniform", 20000, 62), ("lidar", 257, 63)])
 def test_chamfer_forward_backward_equal_reference_kernels(ref_chamfer, kind, n, seed, fixture_clouds):
     a_np, b_np = _clouds(kind, n, seed, fixture_clouds)
     a, b = torch.from_numpy(a_np).cuda().contiguous(), torch.from_numpy(b_np).cuda().contiguous()
     ours, ref = _chamfer(chamfer3d_ext, a, b), _chamfer(ref_chamfer, a, b)
-    for name, x, y in zip(("dist0", "dist1", "idx0", "idx1"), ours, ref):
+    for name, x, y in zip(("idx0", "idx1"), ours[2:], ref[2:]):
         assert torch.equal(x, y), f"{name}: {(x != y).sum().item()} of {x.numel()} differ"
+    for name, x, y in zip(("dist0", "dist1"), ours[:2], ref[:2]):      # fma contraction in the reference binary: <= 2 ulp
+        assert ((x - y).abs() <= 2.5e-7 * y.abs()).all(), f"{name}: max rel {((x - y).abs() / y.abs().clamp_min(1e-30)).max().item()}"
     g0, g1 = torch.rand_like(ours[0]), torch.rand_like(ours[1])
     grads = []
     for mod in (chamfer3d_ext, ref_chamfer):
