@@ -13,7 +13,8 @@
 // to the bounding box) and points outside are stored in the boundary cells -- projection onto a convex box
 // is non-expansive, so every box bound computed from the clamped query stays a valid lower bound.
 // The result is the *exact* nearest neighbour with the reference's tie rule (lowest index), and the
-// squared distance is evaluated with the reference's rounding sequence fma(dz,dz,fma(dy,dy,dx*dx)).
+// squared distance is evaluated with the rounding sequence of the reference's compiled kernel,
+// fma(dz,dz, fma(dx,dx, dy*dy)) (read off the SASS of oracle/_ref/chamfer3D.so: FMUL on dy, FFMA dx, FFMA dz).
 #include "common.cuh"
 #include "himo_b200.h"
 
@@ -290,7 +291,7 @@ __device__ __forceinline__ void nn_scan(const float4* __restrict__ rs, int s, in
   for (int j = s; j < e; ++j) {
     const float4 c = __ldg(rs + j);
     const float dx = c.x - q.x, dy = c.y - q.y, dz = c.z - q.z;
-    const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
     const int ci = __float_as_int(c.w);
     if (d < q.best || (d == q.best && ci < q.best_i)) { q.best = d; q.best_i = ci; }
   }

@@ -143,8 +143,8 @@ def nn_bruteforce_np(query, ref):
     if r.shape[0] == 0:
         return np.full(q.shape[0], 1e20, np.float32), np.full(q.shape[0], -1, np.int32)
     d = (r[None, :, :] - q[:, None, :]).astype(np.float32).astype(np.float64)
-    t = (d[..., 0] * d[..., 0]).astype(np.float32).astype(np.float64)
-    t = (d[..., 1] * d[..., 1] + t).astype(np.float32).astype(np.float64)
+    t = (d[..., 1] * d[..., 1]).astype(np.float32).astype(np.float64)          # dy*dy rounded, then fma dx, fma dz
+    t = (d[..., 0] * d[..., 0] + t).astype(np.float32).astype(np.float64)
     t = (d[..., 2] * d[..., 2] + t).astype(np.float32)
     idx = np.argmin(t, axis=1).astype(np.int32)  # first minimiser = lowest index
     return t[np.arange(q.shape[0]), idx], idx

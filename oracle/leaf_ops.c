@@ -126,9 +126,10 @@ int oracle_dynamic_point_to_voxel(const float *feats, const int64_t *coors, int 
 /* ---- chamfer3D.forward: exact 1-NN, one direction ---------------------------------
  * follows OSF/assets/cuda/chamfer3D/chamfer3D.cu:33-83: best = 1e20, best_i = -1,
  * candidates scanned in ascending index, strict '<' (lowest index wins ties), squared
- * L2 in fp32.  nvcc contracts the reference's expression
+ * L2 in fp32.  nvcc (12.9, sm_100a) contracts the reference's expression
  *   (x1-x0)*(x1-x0) + (y1-y0)*(y1-y0) + (z1-z0)*(z1-z0)
- * left to right into  fma(dz,dz, fma(dy,dy, dx*dx))  -- spelled out here. */
+ * into  fma(dz,dz, fma(dx,dx, dy*dy))  -- FMUL on dy, FFMA dx, FFMA dz in every copy of the loop
+ * body in the SASS of oracle/_ref/chamfer3D.so (oracle/build_ref.py) -- spelled out here. */
 void oracle_nn_bruteforce(const float *q, int nq, const float *r, int nr, float *dist,
                           int32_t *idx) {
 #pragma omp parallel for schedule(static)
@@ -138,7 +139,7 @@ void oracle_nn_bruteforce(const float *q, int nq, const float *r, int nr, float 
     int best_i = -1;
     for (int j = 0; j < nr; ++j) {
       float dx = r[3 * (size_t)j] - x0, dy = r[3 * (size_t)j + 1] - y0, dz = r[3 * (size_t)j + 2] - z0;
-      float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      float d = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
       if (d < best) { best = d; best_i = j; }
     }
     dist[i] = best;
