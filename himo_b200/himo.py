@@ -153,22 +153,30 @@ class InstanceMetrics:
                 for c in ("CAR", "OTHER_VEHICLES")}
 
     def step_eval(self, pc, gt_flow, pc_dt0, gt_category, gt_instance, est_flow=None, est_dis=None):
-        frame = self._blank()
         if est_flow is not None:
-            refine = refine_pts(pc, flow2compDis(est_flow, pc_dt0, sensor_dt=self.sensor_dt))
-        else:
-            refine = refine_pts(pc, est_dis)
-        gt_refine = refine_pts(pc, flow2compDis(gt_flow, pc_dt0, sensor_dt=self.sensor_dt))
+            est_dis = flow2compDis(est_flow, pc_dt0, sensor_dt=self.sensor_dt)
+        self._step(pc, flow2compDis(gt_flow, pc_dt0, sensor_dt=self.sensor_dt), est_dis,
+                   np.linalg.norm(gt_flow, axis=1), gt_category, gt_instance)
+
+    def step_dis(self, pc, gt_dis, est_dis, gt_flow_norm, gt_category, gt_instance):
+        """The same frame step from compensation distances (the offline scorer's inputs: tools/test/score.py:223-360
+        reads `comp_dis`, `gt_flow_norm`, labels and pc0 back from the GT / prediction zips)."""
+        self._step(pc, gt_dis, est_dis, gt_flow_norm, gt_category, gt_instance)
+
+    def _step(self, pc, gt_dis, est_dis, gt_speed, gt_category, gt_instance):
+        frame = self._blank()
+        refine = refine_pts(pc, est_dis)
+        gt_refine = refine_pts(pc, gt_dis)
         for cname in ("CAR", "OTHER_VEHICLES"):
             ids = np.array([CATEGORY_TO_INDEX[c] for c in BUCKETED_METACATAGORIES[cname]])
             mc = np.isin(gt_category, ids)
             if mc.sum() == 0:
                 continue
-            ins_c, flow_c, ref_c, gtref_c, pc_c = gt_instance[mc], gt_flow[mc], refine[mc], gt_refine[mc], pc[mc]
+            ins_c, speed_c, ref_c, gtref_c, pc_c = gt_instance[mc], gt_speed[mc], refine[mc], gt_refine[mc], pc[mc]
             for ins in np.unique(ins_c):
                 m = ins_c == ins
                 npts = int(m.sum())
-                vel = np.linalg.norm(flow_c[m], axis=1).mean() / self.sensor_dt
+                vel = speed_c[m].mean() / self.sensor_dt
                 if npts < 10 or vel < self.min_vel:
                     continue
                 dis = np.linalg.norm(pc_c[m], axis=1).mean()
