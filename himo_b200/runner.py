@@ -83,40 +83,64 @@ def _build_engine(cfg: Dict[str, str], device):
     return SeFlowPPEngine(sd, device=device, precision=cfg.get("precision", "fp32")), 3
 
 
-def run_save(cfg: Dict[str, str]) -> None:
-    """`python save.py checkpoint=... dataset_path=... [res_name=...]` / `python save.py model=fastnsf
-    dataset_path=...` (README.md:47-54; OSF/save.py:25-58, OSF/src/runner.py:316-343)."""
+def shard_frames(n_frames: int, rank: int, world: int) -> range:
+    """Contiguous frame blocks balanced to +-1 frame (2040 frames / 8 ranks = 255 each), where the
+    reference can only deal whole scenes (13 scenes over 8 ranks: 2 + 2 + 2 + 2 + 2 + 1 + 1 + 1)."""
+    return range(rank * n_frames // world, (rank + 1) * n_frames // world)
+
+
+def run_save(cfg: Dict[str, str], engine=None, n_frames: Optional[int] = None) -> int:
+    """`python save.py checkpoint=... dataset_path=... [res_name=...] [shard=frame|scene]` / `python save.py model=fastnsf
+    dataset_path=...` (README.md:47-54; OSF/save.py:25-58, OSF/src/runner.py:316-343).  The reference shards by scene
+    only to keep two processes out of one .h5 file (runner.py:74-80); the per-frame store has no such constraint, so
+    frames are dealt in balanced contiguous blocks unless the store is .h5-backed or `shard=scene` is given.
+    `engine` is injectable for the host tests.  Returns the number of frames this rank wrote."""
     from .dataset import HDF5Dataset
+    from .store import H5Store
     rank, world, local = _dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("himo_b200 needs a CUDA device (no CPU fallback)")
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
     data_dir = cfg.get("dataset_path") or cfg.get("data_dir")
     if not data_dir:
         raise SystemExit("dataset_path=<dir with index_total.pkl and scene files> is required")
-    engine, n_frames = _build_engine(cfg, dev)
-    ds = HDF5Dataset(data_dir, n_frames=n_frames)
+    dev = None
+    if engine is None:
+        if not torch.cuda.is_available():
+            raise SystemExit("himo_b200 needs a CUDA device (no CPU fallback)")
+        dev = torch.device("cuda", local)
+        torch.cuda.set_device(dev)
+        engine, n_frames = _build_engine(cfg, dev)
+    ds = HDF5Dataset(data_dir, n_frames=n_frames or 2)
     res_name = cfg.get("res_name") or (cfg.get("model", "deflowpp") if "model" in cfg else "seflowpp_best")
-    mine = set(shard_scenes(list(ds.scene_id_bounds.keys()), rank, world))
+    shard = cfg.get("shard", "scene" if isinstance(ds.store, H5Store) else "frame")
+    if shard not in ("frame", "scene"):
+        raise SystemExit(f"shard={shard}: frame or scene")
+    if shard == "scene":
+        scenes = set(shard_scenes(list(ds.scene_id_bounds.keys()), rank, world))
+        mine = [i for i, (scene, _) in enumerate(ds.data_index) if scene in scenes]
+    else:
+        mine = shard_frames(len(ds.data_index), rank, world)
     t0, done = time.time(), 0
-    for i, (scene, ts) in enumerate(ds.data_index):
-        if scene not in mine:
-            continue
+    for i in mine:
+        scene, ts = ds.data_index[i]
         item = ds[i]
         if (item["scene_id"], item["timestamp"]) != (scene, ts):
             continue            # clamped duplicate of the neighbouring pair (last frame of a scene)
         final = engine.infer(item)
-        ds.store.write(scene, ts, res_name, final.astype(np.float32))
+        ds.store.write(scene, ts, res_name, np.asarray(final).astype(np.float32))
         done += 1
     if world > 1:
         import torch.distributed as dist
-        if not dist.is_initialized():
-            dist.init_process_group("nccl", device_id=dev)
+        own = not dist.is_initialized()
+        if own:
+            if dev is not None:
+                dist.init_process_group("nccl", device_id=dev)
+            else:
+                dist.init_process_group("gloo")
         dist.barrier()
-        dist.destroy_process_group()
+        if own:
+            dist.destroy_process_group()
     if rank == 0:
-        print(f"[save] wrote '{res_name}' for {done} frames on rank 0 of {world} in {time.time() - t0:.1f}s -> {data_dir}")
+        print(f"[save] wrote '{res_name}' for {done} frames on rank 0 of {world} ({shard} shards) in {time.time() - t0:.1f}s -> {data_dir}")
+    return done
 
 
 def run_save_zip(cfg: Dict[str, str]) -> str:

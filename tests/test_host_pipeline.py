@@ -173,3 +173,42 @@ def test_validate_driver_and_two_rank_merge(dataset_dir, tmp_path):
     assert p.epe_3way["Three-way"] == pytest.approx(0.0, abs=1e-9) and p.epe_3way["IoU"] == pytest.approx(1.0)
     with pytest.raises(SystemExit):
         runner.run_validate({"dataset_path": dataset_dir, "model": "stored", "res_name": "not_there"})
+
+
+class _ScaledGtEngine:
+    def infer(self, item):
+        return item["flow"] * np.float32(0.5)
+
+
+def _save_worker(rank, world, port, data_dir, shard, counts):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = runner.run_save({"dataset_path": data_dir, "res_name": f"half_{shard}", "shard": shard}, engine=_ScaledGtEngine())
+    out = [None] * world
+    dist.all_gather_object(out, n)
+    if rank == 0:
+        np.save(counts, np.array(out))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shard", ["frame", "scene"])
+def test_save_driver_shards_frames_over_two_ranks(tmp_path, shard):
+    """save.py driver with an injected engine: every writable frame is written exactly once across two ranks; frame
+    shards are balanced to one frame where scene shards are as uneven as the scenes (3 scenes over 2 ranks)."""
+    import torch.multiprocessing as mp
+    d = str(tmp_path / "av2_synth")
+    st = store.write_synthetic_dataset(d, n_scenes=3, n_frames=4, n_points=600, seed=13)
+    counts = str(tmp_path / "counts.npy")
+    mp.spawn(_save_worker, args=(2, 29621 + (shard == "scene"), d, shard, counts), nprocs=2, join=True)
+    per_rank = np.load(counts)
+    ds = HDF5Dataset(d, store=st)
+    written = [(s, t) for s, t in ds.data_index if st.has(s, t, f"half_{shard}")]
+    assert per_rank.sum() == len(written) == 9              # the last frame of each scene has no successor
+    for s, t in written:
+        np.testing.assert_array_equal(st.read(s, t, f"half_{shard}"), st.read(s, t, "flow") * np.float32(0.5))
+    if shard == "frame":
+        assert abs(int(per_rank[0]) - int(per_rank[1])) <= 2 and list(runner.shard_frames(2040, 3, 8)) == list(range(765, 1020))
+    else:
+        assert sorted(per_rank.tolist()) == [3, 6]
