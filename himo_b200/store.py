@@ -33,6 +33,9 @@ class FrameStore:
     def write(self, scene: str, ts, name: str, data: np.ndarray) -> None:
         raise NotImplementedError
 
+    def timestamps(self, scene: str) -> List[str]:
+        raise NotImplementedError
+
     def names(self, scene: str, ts) -> List[str]:
         raise NotImplementedError
 
@@ -46,6 +49,9 @@ class NpyStore(FrameStore):
 
     def scenes(self):
         return sorted(d[:-7] for d in os.listdir(self.dir) if d.endswith(".frames"))
+
+    def timestamps(self, scene):
+        return sorted(os.listdir(os.path.join(self.dir, f"{scene}.frames")), key=int)
 
     def has(self, scene, ts, name):
         return os.path.exists(os.path.join(self._frame(scene, ts), name + ".npy"))
@@ -74,6 +80,11 @@ class H5Store(FrameStore):
 
     def scenes(self):
         return sorted(f[:-3] for f in os.listdir(self.dir) if f.endswith(".h5"))
+
+    def timestamps(self, scene):
+        import h5py
+        with h5py.File(self._path(scene), "r") as f:
+            return sorted(f.keys(), key=int)
 
     def has(self, scene, ts, name):
         import h5py
@@ -117,6 +128,20 @@ def read_index(directory: str, name: str = "index_total.pkl") -> List[List]:
 def write_index(directory: str, rows: Sequence[Sequence], name: str = "index_total.pkl") -> None:
     with open(os.path.join(directory, name), "wb") as f:
         pickle.dump([list(r) for r in rows], f)
+
+
+def create_reading_index(directory: str, flow_inside_check: bool = False, store: Optional[FrameStore] = None) -> List[List]:
+    """OSF/dataprocess/misc_data.py:32-55: scan the scenes and write `index_total.pkl` (every frame) or, with
+    `flow_inside_check`, `index_flow.pkl` (frames that carry a ground-truth `flow`); rows are [scene_id, timestamp]
+    with the timestamps of a scene in numeric order."""
+    st = store or open_store(directory)
+    rows = []
+    for scene in st.scenes():
+        for ts in st.timestamps(scene):
+            if not flow_inside_check or st.has(scene, ts, "flow"):
+                rows.append([scene, ts])
+    write_index(directory, rows, "index_flow.pkl" if flow_inside_check else "index_total.pkl")
+    return rows
 
 
 def write_synthetic_dataset(directory: str, n_scenes: int = 2, n_frames: int = 6, n_points: int = 4000,

@@ -212,3 +212,19 @@ def test_save_driver_shards_frames_over_two_ranks(tmp_path, shard):
         assert abs(int(per_rank[0]) - int(per_rank[1])) <= 2 and list(runner.shard_frames(2040, 3, 8)) == list(range(765, 1020))
     else:
         assert sorted(per_rank.tolist()) == [3, 6]
+
+
+def test_create_reading_index_rebuilds_the_indices(tmp_path):
+    """store.create_reading_index (OSF/dataprocess/misc_data.py:32-55): the rebuilt index_total equals the one the
+    writer produced; index_flow lists only frames that carry ground-truth flow; timestamps sort numerically."""
+    d = str(tmp_path / "av2_synth")
+    st = store.write_synthetic_dataset(d, n_scenes=2, n_frames=4, n_points=300, seed=2)
+    want = store.read_index(d, "index_total.pkl")
+    os.remove(os.path.join(d, "index_total.pkl"))
+    assert store.create_reading_index(d, store=st) == sorted(want) == store.read_index(d, "index_total.pkl")
+    scene = want[0][0]
+    st.write(scene, "999", "lidar", np.zeros((1, 4), np.float32))        # a frame without flow, short timestamp
+    total = store.create_reading_index(d, store=st)
+    assert total[0] == [scene, "999"] and len(total) == len(want) + 1     # 999 < 10-digit stamps numerically
+    flow = store.create_reading_index(d, flow_inside_check=True, store=st)
+    assert [scene, "999"] not in flow and len(flow) == len(want) and store.read_index(d, "index_flow.pkl") == flow
