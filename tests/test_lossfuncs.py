@@ -107,3 +107,35 @@ def test_cluster_term_picks_farthest_member_with_dynamic_neighbour():
     s, m = lossfuncs._static_and_cluster_terms(pc0, pc1, est, lab0, lab1, d0, d1, i0, True)
     assert float(s) == pytest.approx(5.0)
     assert float(m) == pytest.approx(0.5)        # |1 - 1.5| for the three members of cluster 2 only
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="needs /root/reference")
+def test_losses_match_live_reference_on_random_label_structures():
+    """Twenty seeded frames with irregular label sets (gaps in the cluster ids, clusters of one point, no static points,
+    no dynamic neighbours at all, duplicated points giving exact distance ties inside a cluster)."""
+    ref = ref_shims.import_lossfuncs()
+    rng = np.random.default_rng(123)
+    for trial in range(20):
+        fr = synth_loss_frame(100 + trial, n=int(rng.integers(700, 1400)), n_clusters=int(rng.integers(1, 30)),
+                              dynamic_fraction=float(rng.uniform(0.3, 0.9)))
+        l0 = fr["pc0_labels"]
+        if trial % 4 == 0:
+            l0[l0 > 1] = l0[l0 > 1] * 7 + 3                  # gaps in the id space
+        if trial % 5 == 1:
+            l0[l0 == 0] = 1                                   # no static points
+        if trial % 5 == 2:
+            fr["pc1_labels"][:] = 0                           # nothing dynamic in pc1: every cluster is skipped
+        if trial % 5 == 3:
+            dyn = torch.nonzero(l0 > 1).squeeze(1)
+            l0[dyn[:5]] = torch.arange(1000, 1005)            # five clusters of a single point
+        if trial % 5 == 4:
+            for c in torch.unique(l0[l0 > 1])[:6]:            # duplicated points: exact distance ties inside a cluster
+                members = torch.nonzero(l0 == c).squeeze(1)
+                if members.numel() >= 2:
+                    fr["pc0"][members[1]] = fr["pc0"][members[0]]
+        for name in ("seflowLoss", "seflowppLoss"):
+            rv, rg = run_loss(getattr(ref, name), fr)
+            v, g = run_loss(getattr(lossfuncs, name), fr, chamfer=CpuChamferDis())
+            for k in TERMS:
+                assert v[k] == pytest.approx(rv[k], rel=2e-6, abs=1e-7), (trial, name, k)
+            np.testing.assert_allclose(g, rg, rtol=0, atol=1e-7, err_msg=f"{trial} {name}")
