@@ -145,6 +145,20 @@ def seflow_losses(cases):
         np.savez_compressed(os.path.join(HERE, f"seflow_loss_s{seed}_n{n}.npz"), **out)
 
 
+def demo_index_shape():
+    """Per-scene row counts of the reference's AV2 demo indices (assets/docs/av2/index_{total,eval}.pkl): config-4 shapes."""
+    import collections
+    import json
+    import pickle
+    base = os.path.join(ref_shims.REFERENCE_ROOT, "assets", "docs", "av2")
+    t = pickle.load(open(os.path.join(base, "index_total.pkl"), "rb"))
+    e = pickle.load(open(os.path.join(base, "index_eval.pkl"), "rb"))
+    c, ce = collections.Counter(s for s, _ in t), collections.Counter(s for s, _ in e)
+    json.dump({"source": "/root/reference/assets/docs/av2/index_{total,eval}.pkl", "total_rows": len(t), "eval_rows": len(e),
+               "frames_per_scene": dict(sorted(c.items())), "eval_frames_per_scene": dict(sorted(ce.items()))},
+              open(os.path.join(HERE, "av2_demo_index_shape.json"), "w"), indent=1)
+
+
 def main():
     assert ref_shims.reference_available(), "needs /root/reference"
     fixture_clouds()
@@ -156,6 +170,7 @@ def main():
     nsfp(models, 6000, 14, 3, 30, 12.0)
     nsfp(models, 6000, 14, 12, 30, 12.0)
     av2_metrics([11, 12, 13])
+    demo_index_shape()
     seflow_losses([(31, 2400, 0.35), (33, 900, 0.5)])
     for name in sorted(os.listdir(HERE)):
         if name.endswith(".npz"):

@@ -228,3 +228,25 @@ def test_create_reading_index_rebuilds_the_indices(tmp_path):
     assert total[0] == [scene, "999"] and len(total) == len(want) + 1     # 999 < 10-digit stamps numerically
     flow = store.create_reading_index(d, flow_inside_check=True, store=st)
     assert [scene, "999"] not in flow and len(flow) == len(want) and store.read_index(d, "index_flow.pkl") == flow
+
+
+def test_config4_index_shapes_and_shard_balance():
+    """BASELINE config 4 (the reference's AV2 demo split): 2040 frames in 13 scenes, 70 eval frames (SURVEY.md 8(c)
+    item 3; tests/golden/av2_demo_index_shape.json from /root/reference/assets/docs/av2/index_*.pkl).  Frame shards put
+    255 frames on each of 8 ranks; the reference's scene shards put between 156 and 314."""
+    import json
+    from conftest import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "av2_demo_index_shape.json")))
+    scenes = sorted(g["frames_per_scene"])
+    assert g["total_rows"] == sum(g["frames_per_scene"].values()) == 2040 and len(scenes) == 13
+    assert g["eval_rows"] == sum(g["eval_frames_per_scene"].values()) == 70
+    if os.path.isdir(os.path.join(REF, "assets", "docs", "av2")):
+        rows = store.read_index(os.path.join(REF, "assets", "docs", "av2"), "index_total.pkl")
+        assert len(rows) == 2040 and {s for s, _ in rows} == set(scenes)
+        assert all(isinstance(t, str) and int(t) > 0 for _, t in rows)
+    per_rank_frame = [len(runner.shard_frames(2040, r, 8)) for r in range(8)]
+    per_rank_scene = [sum(g["frames_per_scene"][s] for s in runner.shard_scenes(scenes, r, 8)) for r in range(8)]
+    assert per_rank_frame == [255] * 8
+    assert sum(per_rank_scene) == 2040 and max(per_rank_scene) >= 313 and min(per_rank_scene) <= 159
+    covered = sorted(i for r in range(8) for i in runner.shard_frames(2040, r, 8))
+    assert covered == list(range(2040))
