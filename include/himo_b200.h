@@ -76,7 +76,9 @@ int himo_dynamic_point_to_voxel_forward(const float* feats, const void* coors, i
  *           OSF/assets/cuda/chamfer3D/chamfer3D_cuda.cpp:18-35, chamfer3D.cu:33-105
  * pc0 [n0,3], pc1 [n1,3] f32 contiguous.  dist* = squared L2 to the nearest point of the other
  * cloud (1e20 when that cloud is empty), idx* = its index (-1 when empty); ties resolve to the
- * lowest index, as the reference's ascending strict-< scan does.  cell_size <= 0 selects the
+ * lowest index, as the reference's ascending strict-< scan does.  The squared distance is rounded
+ * exactly as the compiled reference kernel rounds it: fma(dz,dz, fma(dx,dx, dy*dy)) with d = pc1 - pc0
+ * component differences (sequence read off the reference's sm_100a SASS).  cell_size <= 0 selects the
  * default search cell (0.5 m).
  */
 size_t himo_chamfer_workspace_bytes(int n0, int n1);
