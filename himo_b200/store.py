@@ -144,6 +144,17 @@ def create_reading_index(directory: str, flow_inside_check: bool = False, store:
     return rows
 
 
+def subset_index(full_pkl_path: str, new_folder: str, store: Optional[FrameStore] = None) -> List[List]:
+    """tools/pkl_extract.py: keep the rows of an index whose scene is present in `new_folder` and write the result
+    there under the same file name (how the reference cuts the 13-scene demo split out of the full index)."""
+    with open(full_pkl_path, "rb") as f:
+        rows = pickle.load(f)
+    present = set((store or open_store(new_folder)).scenes())
+    kept = [list(r) for r in rows if r[0] in present]
+    write_index(new_folder, kept, os.path.basename(full_pkl_path))
+    return kept
+
+
 def write_synthetic_dataset(directory: str, n_scenes: int = 2, n_frames: int = 6, n_points: int = 4000,
                             seed: int = 0, eval_every: int = 2, ground_fraction: float = 0.25,
                             store: Optional[FrameStore] = None) -> FrameStore:

@@ -228,6 +228,13 @@ def test_create_reading_index_rebuilds_the_indices(tmp_path):
     assert total[0] == [scene, "999"] and len(total) == len(want) + 1     # 999 < 10-digit stamps numerically
     flow = store.create_reading_index(d, flow_inside_check=True, store=st)
     assert [scene, "999"] not in flow and len(flow) == len(want) and store.read_index(d, "index_flow.pkl") == flow
+    # tools/pkl_extract.py: cut an index down to the scenes present in another folder
+    import shutil
+    demo = str(tmp_path / "demo")
+    os.makedirs(demo)
+    shutil.copytree(os.path.join(d, f"{scene}.frames"), os.path.join(demo, f"{scene}.frames"))
+    kept = store.subset_index(os.path.join(d, "index_total.pkl"), demo)
+    assert kept == [r for r in total if r[0] == scene] == store.read_index(demo, "index_total.pkl") and 0 < len(kept) < len(total)
 
 
 def test_config4_index_shapes_and_shard_balance():
