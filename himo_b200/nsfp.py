@@ -23,7 +23,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .deflowpp import cal_pose0to1, rigid_flow
+from .deflowpp import _Timer, cal_pose0to1, rigid_flow
 
 NSFP_TRUNCATE_SQ = 2        # chamfer3D/__init__.py:78
 
@@ -84,6 +84,7 @@ class NSFP:
         self.verbose = verbose
         self.point_cloud_range = list(point_cloud_range)
         self._chamfer = chamfer
+        self.timer = _Timer()          # the runner touches model.timer[...] (OSF/src/runner.py:141-143, 296)
         self.last_info: Dict = {}
 
     def eval(self):

@@ -37,6 +37,8 @@ def test_prior_state_dict_layout_and_early_stop():
     keys = list(p.state_dict().keys())
     assert keys[:2] == ["nn_layers.0.0.weight", "nn_layers.0.0.bias"] and keys[-2:] == ["nn_layers.16.weight", "nn_layers.16.bias"]
     assert sum(v.numel() for v in p.state_dict().values()) == 3 * 128 + 128 + 7 * (128 * 128 + 128) + 128 * 3 + 3
+    model = nsfp.NSFP(chamfer=CpuChamferDis())
+    model.timer[12].start("One Scan"); model.timer[12].stop(); model.timer.print()      # dztimer-like, as the runner uses it
     es = nsfp._EarlyStop(patience=2, min_delta=0.1)
     assert [es.step(v) for v in (1.0, 0.95, 0.85, 0.84, 0.83)] == [False, False, False, False, True]
     assert nsfp._EarlyStop(patience=3, min_delta=0.0).step(float("nan")) is False       # first value only seeds `best`
