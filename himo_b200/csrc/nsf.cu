@@ -402,7 +402,8 @@ __global__ void k_nsf_control(NsfBufs b, int head_blocks, float min_delta, int p
   c->snapshot = 0;
   if (loss <= c->best_loss) { c->best_loss = loss; c->snapshot = 1; }     // fastnsf.py:151-153
   int stop = 0;
-  if (!c->es_has_best) { c->es_has_best = 1; c->es_best = loss; }
+  if (patience == 0) stop = 0;   // EarlyStopping(patience=0): `self.step = lambda a: False` (nsfp_module.py:60-62), not even NaN stops it
+  else if (!c->es_has_best) { c->es_has_best = 1; c->es_best = loss; }
   else if (isnan(loss)) stop = 1;
   else {
     if (loss < c->es_best - min_delta) { c->es_bad = 0; c->es_best = loss; }

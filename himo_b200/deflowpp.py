@@ -197,11 +197,12 @@ class DeFlowPP:
 
     def forward_triple(self, pch1: torch.Tensor, pc0: torch.Tensor, pc1: torch.Tensor,
                        T_h1: torch.Tensor, T_0: torch.Tensor, compact: bool = True,
-                       stage_events=None) -> Dict[str, torch.Tensor]:
+                       stage_events=None, flow_all_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """One frame triple.  pch1/pc0/pc1: [N,3] f32 CUDA (ground-free, sensor frames);
         T_h1/T_0: [4,4] f32 host transforms into the pc1 frame (cal_pose0to1).
         Returns flow_all [N0,3] (0 where the point was dropped) and, if compact, the reference's
-        compact outputs flow_valid / valid_idx / n_valid (device scalar)."""
+        compact outputs flow_valid / valid_idx / n_valid (device scalar).  `flow_all_out`: caller-owned [>=N0,3] f32
+        CUDA buffer to write flow_all into (the streaming engine passes a preallocated slot; nothing is allocated then)."""
         if self._w is None:
             raise RuntimeError("load_state_dict first")
         for name, t in (("pch1", pch1), ("pc0", pc0), ("pc1", pc1)):
@@ -224,7 +225,12 @@ class DeFlowPP:
             io.n_max = self._n_max
             io.num_iters = self.num_iters
             n0 = pc0.shape[0]
-            flow_all = torch.empty((n0, 3), dtype=torch.float32, device=dev)
+            if flow_all_out is not None:
+                if flow_all_out.dtype != torch.float32 or not flow_all_out.is_contiguous() or flow_all_out.shape[0] < n0:
+                    raise RuntimeError("flow_all_out must be a contiguous float32 [>=N0,3] CUDA tensor")
+                flow_all = flow_all_out[:n0]
+            else:
+                flow_all = torch.empty((n0, 3), dtype=torch.float32, device=dev)
             io.flow_all = flow_all.data_ptr()
             out = {"flow_all": flow_all}
             if compact:

@@ -2,8 +2,10 @@
 
 `SeFlowPPEngine.infer(frame)` is the work of `ModelWrapper.test_step` minus the .h5 write
 (OSF/src/trainer.py:290-343): ground removal, DeFlowPP.forward, pose-flow + network-flow assembly
-for ALL points of pc0.  Inputs are host arrays (as the reference's DataLoader delivers them);
-the H2D copies, the network and the D2H copy of the result run on one CUDA stream per engine.
+for ALL points of pc0.  Inputs are host arrays (as the reference's DataLoader delivers them).
+`infer_stream(frames)` is the multi-frame form every driver uses: two preallocated slots (pinned host
+staging + device buffers) and three CUDA streams per engine, so that the H2D copy of frame i+1 and the
+D2H copy of frame i-1 overlap the network of frame i and no frame allocates memory.
 """
 from __future__ import annotations
 
@@ -16,18 +18,29 @@ from . import _lib
 from .deflowpp import DeFlowPP, cal_pose0to1
 
 
-class _Pinned:
-    """Grow-only pinned host staging buffer."""
+class _Slot:
+    """One in-flight frame of the streaming engine: pinned host staging + device buffers, allocated once
+    (grow-only) so that no frame of a run allocates device or pinned memory."""
 
-    def __init__(self, dtype):
-        self.dtype = dtype
-        self.buf: Optional[torch.Tensor] = None
+    def __init__(self, device, reserve: int):
+        self.device = device
+        self.cap = 0
+        self.reserve = int(reserve)
+        self.ev_net = None                   # the network has finished reading this slot's inputs
+        self.ev_out = None                   # the D2H copy of this slot's result has landed
 
-    def get(self, n: int, cols: int = 3) -> torch.Tensor:
-        need = max(n, 1) * cols
-        if self.buf is None or self.buf.numel() < need:
-            self.buf = torch.empty(int(need * 1.25) + 16, dtype=self.dtype, pin_memory=True)
-        return self.buf[: n * cols].view(n, cols) if cols > 1 else self.buf[:n]
+    def ensure(self, n: int):
+        if n <= self.cap:
+            return
+        cap = max(int(n * 1.25) + 16, self.reserve)
+        dev = self.device
+        self.pin = {k: torch.empty((cap, 3), dtype=torch.float32, pin_memory=True) for k in ("pch1", "pc0", "pc1", "pc0_all", "out")}
+        self.pin_idx = torch.empty(cap, dtype=torch.int32, pin_memory=True)
+        self.pin_T = torch.empty(12, dtype=torch.float32, pin_memory=True)
+        self.dev = {k: torch.empty((cap, 3), dtype=torch.float32, device=dev) for k in ("pch1", "pc0", "pc1", "pc0_all", "flow_all", "final")}
+        self.dev_idx = torch.empty(cap, dtype=torch.int32, device=dev)
+        self.dev_T = torch.empty(12, dtype=torch.float32, device=dev)
+        self.cap = cap
 
 
 class SeFlowPPEngine:
@@ -38,8 +51,8 @@ class SeFlowPPEngine:
         self.net = DeFlowPP(precision=precision, device=self.device, max_points=max_points)
         self.net.load_state_dict(state_dict)
         self.stream = torch.cuda.Stream(self.device)
-        self._pin = {k: _Pinned(torch.float32) for k in ("pch1", "pc0", "pc1", "pc0_all", "out")}
-        self._pin_idx = _Pinned(torch.int32)
+        self._s_in, self._s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self._slots = [_Slot(self.device, max_points) for _ in range(2)]
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -51,139 +64,94 @@ class SeFlowPPEngine:
         keep = ~np.asarray(gm, dtype=bool)
         return pc[keep], keep
 
-    def _upload(self, key: str, arr: np.ndarray) -> torch.Tensor:
-        n = arr.shape[0]
-        pin = self._pin[key].get(n)
-        pin.numpy()[...] = arr
-        dev = torch.empty((n, 3), dtype=torch.float32, device=self.device)
-        dev.copy_(pin, non_blocking=True)
-        self.h2d_bytes += n * 12
-        return dev
-
-    def infer(self, frame: Dict) -> np.ndarray:
-        """frame: pc0, pc1, pch1 [N,>=3] float32; gm0, gm1, gmh1 [N] bool (optional);
-        pose0, pose1, poseh1 [4,4].  Returns final_flow [N0_all, 3] float32: pose flow for every
-        point + network flow on the valid non-ground points (what the reference writes to the .h5)."""
-        self.h2d_bytes = 0
-        self.d2h_bytes = 0
+    # ------------------------------------------------------------------ one frame through a slot
+    def _launch(self, slot: _Slot, frame: Dict):
+        """Stage `frame` into `slot` and enqueue H2D (copy-in stream) -> network + final-flow assembly (compute
+        stream) -> D2H (copy-out stream).  Returns the number of pc0 points; `slot.ev_out` fires when the result is
+        in `slot.pin["out"]`."""
         pc0_all = np.asarray(frame["pc0"], dtype=np.float32)[:, :3]
         pc0, keep0 = self._strip(frame["pc0"], frame.get("gm0"))
         pc1, _ = self._strip(frame["pc1"], frame.get("gm1"))
         pch1, _ = self._strip(frame["pch1"], frame.get("gmh1"))
-        T0 = cal_pose0to1(torch.as_tensor(frame["pose0"]), torch.as_tensor(frame["pose1"]))
+        # pose-flow assembly uses inv(pose1) @ pose0 (OSF/src/trainer.py:320-323); the network warp uses the stored
+        # ego_motion when the frame carries one (wrap_batch_pcs, OSF/src/models/basic/__init__.py:44-50)
+        T_pose = cal_pose0to1(torch.as_tensor(frame["pose0"]), torch.as_tensor(frame["pose1"]))
+        T0 = torch.as_tensor(frame["ego_motion"]).detach().cpu().float() if frame.get("ego_motion") is not None else T_pose
         Th = cal_pose0to1(torch.as_tensor(frame["poseh1"]), torch.as_tensor(frame["pose1"]))
         n_all = pc0_all.shape[0]
-        with torch.cuda.stream(self.stream):
-            d0 = self._upload("pc0", pc0)
-            d1 = self._upload("pc1", pc1)
-            dh = self._upload("pch1", pch1)
+        if slot.ev_out is not None:
+            slot.ev_out.synchronize()           # the previous result of this slot has been consumed by the caller
+        slot.ensure(max(n_all, pc1.shape[0], pch1.shape[0], 1))
+        h2d = 0
+        with torch.cuda.stream(self._s_in):
+            if slot.ev_net is not None:
+                self._s_in.wait_event(slot.ev_net)
+            for key, arr in (("pc0", pc0), ("pc1", pc1), ("pch1", pch1)):
+                n = arr.shape[0]
+                slot.pin[key].numpy()[:n] = arr
+                slot.dev[key][:n].copy_(slot.pin[key][:n], non_blocking=True)
+                h2d += n * 12
             if keep0 is not None:
-                d0_all = self._upload("pc0_all", pc0_all)
-                src = np.full(n_all, -1, np.int32)
+                slot.pin["pc0_all"].numpy()[:n_all] = pc0_all
+                slot.dev["pc0_all"][:n_all].copy_(slot.pin["pc0_all"][:n_all], non_blocking=True)
+                src = slot.pin_idx.numpy()[:n_all]
+                src[...] = -1
                 src[keep0] = np.arange(int(keep0.sum()), dtype=np.int32)
-                pin = self._pin_idx.get(n_all, 1)
-                pin.numpy()[...] = src
-                src_dev = torch.empty(n_all, dtype=torch.int32, device=self.device)
-                src_dev.copy_(pin, non_blocking=True)
-                self.h2d_bytes += n_all * 4
-            else:
-                d0_all, src_dev = d0, None
-            out = self.net.forward_triple(dh, d0, d1, Th, T0, compact=False)
-            T12 = T0[:3, :4].contiguous().float().flatten().to(self.device, non_blocking=True)
-            final = torch.empty((n_all, 3), dtype=torch.float32, device=self.device)
-            st = _lib.lib().himo_final_flow(_lib.ptr(d0_all), n_all, _lib.ptr(T12), _lib.ptr(out["flow_all"]),
-                                            _lib.ptr(src_dev), _lib.ptr(final), _lib.stream_ptr(self.device))
+                slot.dev_idx[:n_all].copy_(slot.pin_idx[:n_all], non_blocking=True)
+                h2d += n_all * 16
+            slot.pin_T.numpy()[...] = T_pose[:3, :4].contiguous().float().flatten().numpy()
+            slot.dev_T.copy_(slot.pin_T, non_blocking=True)
+            h2d += 48
+            ev_in = torch.cuda.Event()
+            ev_in.record(self._s_in)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev_in)
+            d0 = slot.dev["pc0"][:pc0.shape[0]]
+            self.net.forward_triple(slot.dev["pch1"][:pch1.shape[0]], d0, slot.dev["pc1"][:pc1.shape[0]], Th, T0,
+                                    compact=False, flow_all_out=slot.dev["flow_all"])
+            d0_all = slot.dev["pc0_all"] if keep0 is not None else slot.dev["pc0"]
+            st = _lib.lib().himo_final_flow(_lib.ptr(d0_all), n_all, _lib.ptr(slot.dev_T), _lib.ptr(slot.dev["flow_all"]),
+                                            _lib.ptr(slot.dev_idx) if keep0 is not None else None,
+                                            _lib.ptr(slot.dev["final"]), _lib.stream_ptr(self.device))
             _lib.check(st, "himo_final_flow")
-            host = self._pin["out"].get(n_all)
-            host.copy_(final, non_blocking=True)
-            self.d2h_bytes += n_all * 12
-        self.stream.synchronize()
-        return host.numpy().copy()
+            slot.ev_net = torch.cuda.Event()
+            slot.ev_net.record(self.stream)
+        with torch.cuda.stream(self._s_out):
+            self._s_out.wait_event(slot.ev_net)
+            slot.pin["out"][:n_all].copy_(slot.dev["final"][:n_all], non_blocking=True)
+            slot.ev_out = torch.cuda.Event()
+            slot.ev_out.record(self._s_out)
+        self.h2d_bytes, self.d2h_bytes = h2d, n_all * 12
+        return n_all
+
+    @staticmethod
+    def _collect(slot: _Slot, n_all: int) -> np.ndarray:
+        slot.ev_out.synchronize()
+        out = slot.pin["out"].numpy()[:n_all].copy()
+        slot.ev_out = None
+        return out
+
+    def infer(self, frame: Dict) -> np.ndarray:
+        """frame: pc0, pc1, pch1 [N,>=3] float32; gm0, gm1, gmh1 [N] bool (optional); pose0, pose1, poseh1 [4,4];
+        ego_motion [4,4] (optional).  Returns final_flow [N0_all, 3] float32: pose flow for every point + network
+        flow on the valid non-ground points (what the reference writes to the .h5).  One frame, synchronous."""
+        slot = self._slots[0]
+        return self._collect(slot, self._launch(slot, frame))
 
     # ------------------------------------------------------------------ pipelined streaming API
     def infer_stream(self, frames):
         """Iterate over host frames and yield `final_flow` arrays in order, with the H2D copy of frame i+1
-        and the D2H copy of frame i-1 overlapping the network of frame i (three CUDA streams, two slots).
-        Same results as `infer`; this is the call the multi-frame drivers (runner.run_save, bench.py) use."""
-        dev = self.device
-        if not hasattr(self, "_s_in"):
-            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-            self._slots = [dict(pin={k: _Pinned(torch.float32) for k in ("pch1", "pc0", "pc1", "pc0_all", "out")},
-                                pin_idx=_Pinned(torch.int32)) for _ in range(2)]
-        pending = []          # (slot, ev_out, n_all)
-        ev_done = [None, None]
-
-        def launch(i, frame):
-            slot = self._slots[i % 2]
-            pc0_all = np.asarray(frame["pc0"], dtype=np.float32)[:, :3]
-            pc0, keep0 = self._strip(frame["pc0"], frame.get("gm0"))
-            pc1, _ = self._strip(frame["pc1"], frame.get("gm1"))
-            pch1, _ = self._strip(frame["pch1"], frame.get("gmh1"))
-            T0 = cal_pose0to1(torch.as_tensor(frame["pose0"]), torch.as_tensor(frame["pose1"]))
-            Th = cal_pose0to1(torch.as_tensor(frame["poseh1"]), torch.as_tensor(frame["pose1"]))
-            n_all = pc0_all.shape[0]
-            h2d = d2h = 0
-            with torch.cuda.stream(self._s_in):
-                if ev_done[i % 2] is not None:          # the network has finished reading this slot's inputs
-                    self._s_in.wait_event(ev_done[i % 2])
-                devs = {}
-                for key, arr in (("pc0", pc0), ("pc1", pc1), ("pch1", pch1)):
-                    pin = slot["pin"][key].get(arr.shape[0])
-                    pin.numpy()[...] = arr
-                    d = torch.empty((arr.shape[0], 3), dtype=torch.float32, device=dev)
-                    d.copy_(pin, non_blocking=True)
-                    devs[key] = d
-                    h2d += arr.shape[0] * 12
-                if keep0 is not None:
-                    pin = slot["pin"]["pc0_all"].get(n_all)
-                    pin.numpy()[...] = pc0_all
-                    d0_all = torch.empty((n_all, 3), dtype=torch.float32, device=dev)
-                    d0_all.copy_(pin, non_blocking=True)
-                    src = np.full(n_all, -1, np.int32)
-                    src[keep0] = np.arange(int(keep0.sum()), dtype=np.int32)
-                    pidx = slot["pin_idx"].get(n_all, 1)
-                    pidx.numpy()[...] = src
-                    src_dev = torch.empty(n_all, dtype=torch.int32, device=dev)
-                    src_dev.copy_(pidx, non_blocking=True)
-                    h2d += n_all * 16
-                else:
-                    d0_all, src_dev = devs["pc0"], None
-                T12 = T0[:3, :4].contiguous().float().flatten().pin_memory().to(dev, non_blocking=True)
-                ev_in = torch.cuda.Event()
-                ev_in.record(self._s_in)
-            with torch.cuda.stream(self.stream):
-                self.stream.wait_event(ev_in)
-                out = self.net.forward_triple(devs["pch1"], devs["pc0"], devs["pc1"], Th, T0, compact=False)
-                final = torch.empty((n_all, 3), dtype=torch.float32, device=dev)
-                st = _lib.lib().himo_final_flow(_lib.ptr(d0_all), n_all, _lib.ptr(T12), _lib.ptr(out["flow_all"]),
-                                                _lib.ptr(src_dev), _lib.ptr(final), _lib.stream_ptr(dev))
-                _lib.check(st, "himo_final_flow")
-                ev = torch.cuda.Event()
-                ev.record(self.stream)
-                ev_done[i % 2] = ev
-                for t in list(devs.values()) + [d0_all, T12, final] + ([src_dev] if src_dev is not None else []):
-                    t.record_stream(self.stream)
-            with torch.cuda.stream(self._s_out):
-                self._s_out.wait_event(ev)
-                host = slot["pin"]["out"].get(n_all)
-                host.copy_(final, non_blocking=True)
-                final.record_stream(self._s_out)
-                ev_out = torch.cuda.Event()
-                ev_out.record(self._s_out)
-            self.h2d_bytes, self.d2h_bytes = h2d, n_all * 12
-            return (host, ev_out)
-
-        def collect(item):
-            host, ev_out = item
-            ev_out.synchronize()
-            return host.numpy().copy()
-
+        and the D2H copy of frame i-1 overlapping the network of frame i (three CUDA streams, two preallocated
+        slots).  Same results as `infer`.  This is the call bench.py's `e2e` arm times and the one the multi-frame
+        drivers (runner.run_save, runner.run_validate) go through."""
+        pending = []          # (slot, n_all)
         for i, frame in enumerate(frames):
-            pending.append(launch(i, frame))
+            slot = self._slots[i % 2]
+            pending.append((slot, self._launch(slot, frame)))
             if len(pending) == 2:            # the slot about to be reused must be drained first
-                yield collect(pending.pop(0))
+                yield self._collect(*pending.pop(0))
         while pending:
-            yield collect(pending.pop(0))
+            yield self._collect(*pending.pop(0))
 
 
 class FastNSFEngine:

@@ -1,17 +1,24 @@
 """Drivers behind the command lines kept from the reference: `save.py` (flow -> <res_name> in the frame
 store), `save_zip.py` (flow -> compensation-distance zip) and `eval.py` (HiMo instance metrics).
 
-Multi-GPU: one process per GPU (torchrun, or `gpus=N` which spawns them), scenes sharded round-robin
-over the ranks exactly like `SceneDistributedSampler` (OSF/src/runner.py:38-88: all frames of a scene stay
-on one rank, so no two processes ever write the same scene file); the only collective is the metric
-gather at the end (runner.py:249-256).
+Multi-GPU: one process per GPU -- under torchrun, or `gpus=N` on the command line, which spawns N ranks on this node
+the way the reference's `launch_runner` does with mp.spawn (OSF/src/runner.py:316-343).  Frames are dealt in balanced
+contiguous blocks (`shard=frame`) or whole scenes like `SceneDistributedSampler` (`shard=scene`, OSF/src/runner.py:38-88);
+the only collective is the metric gather at the end (runner.py:249-256).
+
+Per rank the frame loop is a three-stage pipeline: a reader thread prefetches frames from the store, the engine's
+`infer_stream` overlaps H2D / network / D2H on three CUDA streams, and a writer thread puts results into the store --
+the same `infer_stream` call bench.py's `e2e` arm times.
 """
 from __future__ import annotations
 
 import os
+import queue
 import sys
+import threading
 import time
-from typing import Dict, List, Optional
+from collections import deque
+from typing import Callable, Dict, Iterable, Iterator, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -42,6 +49,97 @@ def parse_overrides(argv: List[str], aliases: Optional[Dict[str, str]] = None) -
         out[aliases.get(k, k)] = v
         i += 1
     return out
+
+
+class _Prefetch:
+    """Reader thread: `fetch(i)` for i in `indices`, up to `depth` frames ahead of the consumer (the reference gets the
+    same overlap from DataLoader workers, OSF/src/runner.py:123-127)."""
+
+    def __init__(self, fetch: Callable[[int], Dict], indices: Iterable[int], depth: int = 4):
+        self.q: "queue.Queue" = queue.Queue(maxsize=depth)
+        self.t = threading.Thread(target=self._run, args=(fetch, list(indices)), daemon=True)
+        self.t.start()
+
+    def _run(self, fetch, indices):
+        try:
+            for i in indices:
+                self.q.put((i, fetch(i)))
+            self.q.put(None)
+        except BaseException as e:              # surfaced in the consumer, never swallowed
+            self.q.put(e)
+
+    def __iter__(self) -> Iterator[Tuple[int, Dict]]:
+        while True:
+            it = self.q.get()
+            if it is None:
+                return
+            if isinstance(it, BaseException):
+                raise it
+            yield it
+
+
+class _Writer:
+    """Writer thread: store writes leave the frame loop (the reference writes synchronously, OSF/src/trainer.py:337-343)."""
+
+    def __init__(self, write: Callable, depth: int = 8):
+        self.q: "queue.Queue" = queue.Queue(maxsize=depth)
+        self.err: Optional[BaseException] = None
+        self.write = write
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        while True:
+            it = self.q.get()
+            if it is None:
+                return
+            if self.err is None:
+                try:
+                    self.write(*it)
+                except BaseException as e:
+                    self.err = e
+
+    def put(self, *args):
+        if self.err is not None:
+            raise self.err
+        self.q.put(args)
+
+    def close(self):
+        self.q.put(None)
+        self.t.join()
+        if self.err is not None:
+            raise self.err
+
+
+def infer_many(engine, items: Iterable[Dict]) -> Iterator[Tuple[Dict, np.ndarray]]:
+    """(item, final_flow) for every item, in order, through the engine's pipelined `infer_stream` when it has one."""
+    if not hasattr(engine, "infer_stream"):
+        for item in items:
+            yield item, engine.infer(item)
+        return
+    seen: deque = deque()
+
+    def tee():
+        for item in items:
+            seen.append(item)
+            yield item
+    for final in engine.infer_stream(tee()):
+        yield seen.popleft(), final
+
+
+def _ensure_group(local: int, need_cuda: bool):
+    """Process group for the end-of-run metric gather / barrier.  NCCL with this rank's own device when the run uses
+    GPUs (the device is set BEFORE the group exists, otherwise every rank would sit on cuda:0), gloo for host-only runs."""
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return False
+    if need_cuda and torch.cuda.is_available() and local < torch.cuda.device_count():
+        dev = torch.device("cuda", local)
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo")
+    return True
 
 
 def _dist_env():
@@ -119,22 +217,22 @@ def run_save(cfg: Dict[str, str], engine=None, n_frames: Optional[int] = None) -
     else:
         mine = shard_frames(len(ds.data_index), rank, world)
     t0, done = time.time(), 0
-    for i in mine:
-        scene, ts = ds.data_index[i]
-        item = ds[i]
-        if (item["scene_id"], item["timestamp"]) != (scene, ts):
-            continue            # clamped duplicate of the neighbouring pair (last frame of a scene)
-        final = engine.infer(item)
-        ds.store.write(scene, ts, res_name, np.asarray(final).astype(np.float32))
-        done += 1
+
+    def own_frames():
+        for i, item in _Prefetch(ds.__getitem__, mine):
+            if (item["scene_id"], item["timestamp"]) == tuple(ds.data_index[i]):
+                yield item      # else: clamped duplicate of the neighbouring pair (last frame of a scene)
+
+    writer = _Writer(ds.store.write)
+    try:
+        for item, final in infer_many(engine, own_frames()):
+            writer.put(item["scene_id"], item["timestamp"], res_name, np.asarray(final, dtype=np.float32))
+            done += 1
+    finally:
+        writer.close()
     if world > 1:
         import torch.distributed as dist
-        own = not dist.is_initialized()
-        if own:
-            if dev is not None:
-                dist.init_process_group("nccl", device_id=dev)
-            else:
-                dist.init_process_group("gloo")
+        own = _ensure_group(local, dev is not None)
         dist.barrier()
         if own:
             dist.destroy_process_group()
@@ -169,7 +267,7 @@ def run_eval(cfg: Dict[str, str]):
     res_name = cfg.get("res_name", "")
     zip_path = cfg.get("comp_dis_zip", "")
     data_name, flag = himo.check_valid(data_dir, res_name, zip_path)
-    rank, world, _ = _dist_env()
+    rank, world, local = _dist_env()
     metrics = himo.InstanceMetrics(data_name)
     ds = HDF5Dataset(data_dir, vis_name=res_name if flag == 2 else "", eval=True)
     for i in range(rank, len(ds), world):
@@ -189,8 +287,7 @@ def run_eval(cfg: Dict[str, str]):
                               data["flow_instance_id"][m], est_dis=comp[m])
     if world > 1:
         import torch.distributed as dist
-        if not dist.is_initialized():
-            dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        _ensure_group(local, True)
         gathered = [None] * world if rank == 0 else None
         dist.gather_object(metrics, gathered, dst=0)
         if rank == 0:
@@ -248,9 +345,9 @@ def run_validate(cfg: Dict[str, str], engine=None, n_frames: Optional[int] = Non
                                                        cfg.get("output", f"{cfg.get('model', 'deflowpp')}-{data_mode}-v{version}"))
     metrics = M.OfficialMetrics()
     t0, done = time.time(), 0
-    for i in range(rank, len(ds), world):
-        item = ds[i]
-        final = np.asarray(engine.infer(item), np.float32)
+    frames_it = (item for _, item in _Prefetch(ds.__getitem__, range(rank, len(ds), world)))
+    for item, final in infer_many(engine, frames_it):
+        final = np.asarray(final, np.float32)
         pc0 = np.asarray(item["pc0"], np.float32)[:, :3]
         pose_flow = himo.pose_flow_np(pc0, item["pose0"], item["pose1"]).astype(np.float32)
         m = np.asarray(item["eval_mask"], bool).squeeze()
@@ -266,8 +363,7 @@ def run_validate(cfg: Dict[str, str], engine=None, n_frames: Optional[int] = Non
         done += 1
     if world > 1:
         import torch.distributed as dist
-        if not dist.is_initialized():
-            dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        _ensure_group(local, True)
         gathered = [None] * world if rank == 0 else None
         dist.gather_object(metrics, gathered, dst=0)
         if rank == 0:
@@ -295,8 +391,36 @@ def run_validate(cfg: Dict[str, str], engine=None, n_frames: Optional[int] = Non
     return metrics
 
 
+def _spawn_rank(rank: int, world: int, port: int, fn_name: str, cfg: Dict[str, str]):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    globals()[fn_name](cfg)
+
+
+def _launch(fn_name: str, cfg: Dict[str, str]):
+    """`gpus=N` (N > 1) outside torchrun: spawn N ranks on this node, one per GPU (launch_runner, OSF/src/runner.py:
+    316-343: mp.spawn over torch.cuda.device_count()).  Under torchrun, or with gpus=1 / absent, run in this process."""
+    gpus = cfg.pop("gpus", None)
+    n = 1
+    if gpus is not None:
+        n = torch.cuda.device_count() if str(gpus) in ("all", "-1") else int(gpus)
+        if n < 1:
+            raise SystemExit(f"gpus={gpus}: need a positive GPU count")
+    if n > 1 and "WORLD_SIZE" not in os.environ:
+        if torch.cuda.is_available() and n > torch.cuda.device_count():
+            raise SystemExit(f"gpus={n} but this node has {torch.cuda.device_count()} CUDA device(s)")
+        import socket
+        import torch.multiprocessing as mp
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        mp.spawn(_spawn_rank, args=(n, port, fn_name, cfg), nprocs=n, join=True)
+        return None
+    return globals()[fn_name](cfg)
+
+
 def main_save(argv=None):
-    run_save(parse_overrides(sys.argv[1:] if argv is None else argv))
+    return _launch("run_save", parse_overrides(sys.argv[1:] if argv is None else argv))
 
 
 def main_save_zip(argv=None):
@@ -308,5 +432,5 @@ def main_eval(argv=None):
     the hydra way (`checkpoint=` / `model=`), OpenSceneFlow's eval.py (scene-flow metrics of a fresh model run)."""
     cfg = parse_overrides(sys.argv[1:] if argv is None else argv, aliases={"flow_mode": "res_name"})
     if "checkpoint" in cfg or "model" in cfg:
-        return run_validate(cfg)
-    return run_eval(cfg)
+        return _launch("run_validate", cfg)
+    return _launch("run_eval", cfg)

@@ -5,7 +5,7 @@
 # 2. the whole -m gpu suite, 3. smoke(), 4. the bench line, 5. the side-by-side bench against the reference kernels.
 set -u
 mkdir -p gpurun_out
-HIMO_TEST_REF_KERNELS=1 timeout 90 python -m pytest tests/test_gpu_vs_reference_kernels.py -m gpu -q > gpurun_out/checkin_ref_kernels.log 2>&1
+timeout 90 python -m pytest tests/test_gpu_vs_reference_kernels.py -m gpu -q > gpurun_out/checkin_ref_kernels.log 2>&1
 tail -3 gpurun_out/checkin_ref_kernels.log
 timeout 240 python -m pytest tests -m gpu -q > gpurun_out/checkin_gpu_tests.log 2>&1
 tail -3 gpurun_out/checkin_gpu_tests.log

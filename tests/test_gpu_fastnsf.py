@@ -137,3 +137,13 @@ def test_against_reference_class_golden(path):
         assert d.max() <= 1e-4, d.max()
     else:
         assert d.mean() <= 4e-3 and d.max() <= 2e-2, (d.mean(), d.max())
+
+
+def test_patience_zero_never_stops_early():
+    """EarlyStopping(patience=0) replaces step by `lambda a: False` (nsfp_module.py:60-62): the loop runs itr_num iterations."""
+    tr = frames.lidar_triple(2000, 9)
+    net = fastnsf.FastNSF(itr_num=7, early_patience=0, min_delta=1e9)
+    batch = {"pc0": torch.from_numpy(tr["pc0"])[None].cuda(), "pc1": torch.from_numpy(tr["pc1"])[None].cuda(),
+             "pose0": [torch.from_numpy(tr["pose0"])], "pose1": [torch.from_numpy(tr["pose1"])]}
+    net(batch)
+    assert net.last_info["iterations"] == 7

@@ -8,11 +8,10 @@ Measured on a B200 (profiles/r01_ref_kernels_vs_ours.json, profiles/r01_ref_kern
 scatter maps / counts / voxel order and ALL nearest-neighbour indices (376 k queries) bit-equal; voxel means differ by
 2.4e-7 (atomics order); the squared distances differed in the last bit for a share of the points because the kernel and
 oracle/leaf_ops.c then rounded fma(dz,dz, fma(dy,dy, dx*dx)) where the reference binary (SASS of
-oracle/_ref/chamfer3D.so) computes fma(dz,dz, fma(dx,dx, dy*dy)).  Both were changed to the binary's sequence after that
-run; the Chamfer test below therefore demands strict equality again and stays opt-in (HIMO_TEST_REF_KERNELS=1) until it
-has run once more on a B200.  The voxelize / scatter test passed as written."""
-import os
-
+oracle/_ref/chamfer3D.so) computes fma(dz,dz, fma(dx,dx, dy*dy)).  Both were changed to the binary's sequence; the
+re-run at the start of round 2 (profiles/r02_ref_kernels_strict_tests.log, profiles/r02_ref_kernels_vs_ours.json) then
+found every index AND every squared distance bit-equal to the reference binary (0 mismatches in 376 k queries), so the
+Chamfer test demands strict equality and runs in the normal -m gpu suite."""
 import numpy as np
 import pytest
 import torch
@@ -20,8 +19,6 @@ import torch
 from himo_b200 import chamfer3d_ext, frames, mmcv_ext
 from oracle import build_ref
 
-opt_in = pytest.mark.skipif(os.environ.get("HIMO_TEST_REF_KERNELS", "0") != "1",
-                            reason="opt-in until verified on a B200: HIMO_TEST_REF_KERNELS=1")
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not (build_ref.built("chamfer3D") and build_ref.built("mmcv")),
                                  reason="oracle/_ref/*.so not built (python -m oracle.build_ref)")]
@@ -54,7 +51,6 @@ def _chamfer(mod, a, b):
     return d0, d1, i0, i1
 
 
-@opt_in
 @pytest.mark.parametrize("kind,n,seed", [("fixture", 0, 0), ("lidar", 30000, 61), ("uniform", 20000, 62), ("lidar", 257, 63)])
 def test_chamfer_forward_backward_equal_reference_kernels(ref_chamfer, kind, n, seed, fixture_clouds):
     a_np, b_np = _clouds(kind, n, seed, fixture_clouds)
