@@ -192,6 +192,8 @@ def main():
     net = eng.net
     host_frames = make_frames(rank, 2)
     L = _lib.lib()
+    if os.environ.get("HIMO_PDL") is not None:          # A/B knob (profiles/): programmatic dependent launch on / off
+        L.himo_conv_set_pdl(int(os.environ["HIMO_PDL"]))
 
     # ---- device-resident copies for the kernel-only arm
     dev_frames = []

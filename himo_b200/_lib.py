@@ -79,7 +79,34 @@ def ptr(t):
 def stream_ptr(device=None) -> c_void_p:
     """The caller's current CUDA stream, as the reference's ops use
     (at::cuda::getCurrentCUDAStream(), e.g. OSF/assets/cuda/chamfer3D/chamfer3D.cu:88)."""
+    if _raw_stream is not None:
+        idx = device.index if isinstance(device, torch.device) else device
+        if isinstance(idx, int):
+            return c_void_p(_raw_stream(idx))          # ~0.3 us instead of ~2 us through the Stream object
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def on_device(device):
+    """`with on_device(t.device):` -- the device guard of the reference's ops (CUDAGuard, voxelization_cuda.cu:253)
+    without the ~4 us of torch.cuda.device when `device` is already current (the common, single-GPU-per-process case)."""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(device)
 
 
 def require_cuda(t: torch.Tensor, name: str) -> None:

@@ -35,7 +35,7 @@ def forward(pc0, pc1, dist0, dist1, idx0, idx1) -> int:
     L = _lib.lib()
     dev = pc0.device
     ws_bytes = L.himo_chamfer_workspace_bytes(n0, n1)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         ws = _lib.workspace.get(ws_bytes, dev)
         st = L.himo_chamfer_forward(_lib.ptr(pc0), n0, _lib.ptr(pc1), n1, _lib.ptr(dist0),
                                     _lib.ptr(dist1), _lib.ptr(idx0), _lib.ptr(idx1),
@@ -63,7 +63,7 @@ def forward_radius(pc0, pc1, dist0, dist1, idx0, idx1, radius: float) -> int:
     L = _lib.lib()
     dev = pc0.device
     ws_bytes = L.himo_chamfer_workspace_bytes(n0, n1)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         ws = _lib.workspace.get(ws_bytes, dev)
         st = L.himo_chamfer_forward_radius(_lib.ptr(pc0), n0, _lib.ptr(pc1), n1, _lib.ptr(dist0),
                                            _lib.ptr(dist1), _lib.ptr(idx0), _lib.ptr(idx1),
@@ -84,7 +84,7 @@ def backward(pc0, pc1, idx0, idx1, grad_dist0, grad_dist1, grad_pc0, grad_pc1) -
     _chk(grad_pc0, "grad_pc0", torch.float32, 3)
     _chk(grad_pc1, "grad_pc1", torch.float32, 3)
     dev = pc0.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         st = _lib.lib().himo_chamfer_backward(
             _lib.ptr(pc0), pc0.shape[0], _lib.ptr(pc1), pc1.shape[0], _lib.ptr(idx0), _lib.ptr(idx1),
             _lib.ptr(grad_dist0), _lib.ptr(grad_dist1), _lib.ptr(grad_pc0), _lib.ptr(grad_pc1),

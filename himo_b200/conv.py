@@ -27,6 +27,7 @@ class ConvDesc(ctypes.Structure):
         ("stop_flag", c_void_p),
         ("aux_h", c_void_p), ("aux_z", c_void_p), ("aux_ld", c_int),
         ("out2", c_void_p), ("out2_plane_stride", c_longlong), ("out2_ld", c_int),
+        ("border_bias", c_void_p),
     ]
 
 
@@ -76,7 +77,7 @@ def pack_conv_weight(w: torch.Tensor, planes: int, prescale: float = 1.0) -> tor
 def conv2d_nhwc(x_planes: torch.Tensor, w_planes: torch.Tensor, bias, out: torch.Tensor, *, ksize: int,
                 stride: int = 1, act: int = 0, cin_off: int = 0, cin: int | None = None, cout_off: int = 0,
                 n_groups: int = 1, cin_group_stride: int = 0, cout_group_stride: int = 0,
-                acc_scale: float = 1.0) -> None:
+                acc_scale: float = 1.0, border_bias: torch.Tensor | None = None) -> None:
     """x_planes [P,H,W,Cin_total] bf16; w_planes [P,Cout,K] bf16; out [Po,Ho,Wo,Cout_total] bf16 or
     [Ho,Wo,Cout_total] fp32 (written in place)."""
     P, H, W, Ct = x_planes.shape
@@ -97,6 +98,7 @@ def conv2d_nhwc(x_planes: torch.Tensor, w_planes: torch.Tensor, bias, out: torch
         d.Cout_total = out.shape[3]
     d.cout_off = cout_off; d.act = act; d.acc_scale = acc_scale
     d.n_groups = n_groups; d.cin_group_stride = cin_group_stride; d.cout_group_stride = cout_group_stride
+    d.border_bias = border_bias.data_ptr() if border_bias is not None else None     # [3,3,Cout] f32 (composed 1x1 -> 3x3)
     dev = x_planes.device
     with torch.cuda.device(dev):
         st = _lib.lib().himo_conv2d_nhwc(ctypes.byref(d), _lib.stream_ptr(dev))

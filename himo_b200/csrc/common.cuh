@@ -49,6 +49,14 @@ struct Arena {
   __host__ bool ok() const { return off <= cap && (base != nullptr || off == 0); }
 };
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in
+// the stream is still running; pdl_wait() blocks until that predecessor has completed and its memory is visible
+// (a no-op for a normal launch).  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as
+// every CTA of this grid has called it (they still block in their own pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- streaming 128-bit accesses -------------------------------------------------------
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 r;

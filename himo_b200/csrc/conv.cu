@@ -48,7 +48,6 @@ struct ConvParams {
   int act, out_fp32;
   float acc_scale;
   int flush_stages;
-  int a_tmem;                        // split mode: stage the A slices in tensor memory (tcgen05.cp + .ts MMAs)
   // GEMM-epilogue extensions used by the FastNSF MLP (csrc/nsf.cu)
   __nv_bfloat16* out_t;            // optional transposed copy: [planes][Cout_total][ld_t], column = pixel
   long long out_t_plane_stride;
@@ -66,6 +65,11 @@ struct ConvParams {
   __nv_bfloat16* out2;             // split-plane operand buffer of the NEXT GEMM ([planes][pixels][out2_ld])
   long long out2_plane_stride;
   int out2_ld;
+  // composed 1x1 -> 3x3 convolutions (deflowpp.cu): bias per border class [3][3][Cout] (row class, column class;
+  // 0 = first row/column, 1 = interior, 2 = last), used instead of `bias` for pixels on the image border
+  const float* border_bias;
+  int H_out;
+  long long* dbg;                  // optional per-tile clock64() trace [CTA][32 tiles][8] (himo_conv_set_debug_buffer)
 };
 
 // sigmoid / tanh through ex2.approx + fast division: abs error ~2e-7, far below the 1e-4 flow budget, and
@@ -75,8 +79,25 @@ __device__ __forceinline__ float fast_tanh(float x) {
   const float e = __expf(-2.0f * fabsf(x));
   return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
 }
+// Exact-erf GELU (nn.GELU(), basic/__init__.py:76-94) without erff's branches: 0.5 x (1 + erf(x/sqrt2)) = 0.5 x erfc(-x/sqrt2),
+// erfc(t) = 2^p(t) for t = |x|/sqrt2 in [0, 5] with p a degree-8 minimax fit of log2(erfc) weighted for uniform ABSOLUTE
+// error of erfc (5.9e-8 in fp32 Horner form + ex2.approx's 2^-22 relative).  |GELU error| <= 3e-7 max(|x|, 1) -- below
+// the 1.1e-6 of torch's own fp32 CPU GELU against the exact function on [-12, 12] -- in 13 instructions instead of ~35
+// (the epilogue warps were issue-bound on erff: profiles/r02_conv_tile_trace.txt).
 __device__ __forceinline__ float gelu_erf(float v) {
-  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  const float t = fminf(fabsf(v) * 0.70710678118654752440f, 5.0f);
+  float p = -4.535873086e-05f;
+  p = __fmaf_rn(p, t, 4.455077578e-04f);
+  p = __fmaf_rn(p, t, -1.489439164e-03f);
+  p = __fmaf_rn(p, t, -7.746376796e-04f);
+  p = __fmaf_rn(p, t, 2.825369127e-02f);
+  p = __fmaf_rn(p, t, -1.484816223e-01f);
+  p = __fmaf_rn(p, t, -9.184163809e-01f);
+  p = __fmaf_rn(p, t, -1.627908587e+00f);
+  float e;                                            // 2^(p t) in [2^-46, 1]: one MUFU.EX2, no range fix-up needed
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p * t));
+  const float h = 0.5f * v * e;                       // 0.5 x erfc(|x|/sqrt2)
+  return v > 0.f ? v - h : h;
 }
 
 // Pipeline stage = one A load shared by NX taps + the NX weight tiles.
@@ -112,10 +133,9 @@ struct ConvCfg {
   static constexpr int kMaxBias = 1024;
   static constexpr int kTotal = kBiasOffset + kMaxBias * 4 + 128;   // barriers + bias + alignment slack
   // split mode: 2 main + 1 or 2 cross accumulators, then 8 staging slots x 16 columns for the A slices in TMEM
-  static constexpr int kCrossBufs = (P == 2 && 4 * BN + 128 <= 512) ? 2 : 1;
+  static constexpr int kCrossBufs = (P == 2 && 4 * BN <= 512) ? 2 : 1;
   static constexpr int kAccCols = P == 2 ? (2 + kCrossBufs) * BN : 2 * BN;
-  static constexpr int kStageCol = kAccCols;
-  static constexpr int kUsedCols = P == 2 ? kAccCols + 128 : kAccCols;
+  static constexpr int kUsedCols = kAccCols;
   static constexpr int kTmemCols = kUsedCols <= 64 ? 64 : kUsedCols <= 128 ? 128 : kUsedCols <= 256 ? 256 : 512;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
@@ -379,7 +399,10 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   float* bias_smem = (float*)(smem + C::kBiasOffset);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (p.stop_flag && *p.stop_flag) return;   // uniform across the grid
+  if (p.stop_flag) {                         // the flag is written by an earlier kernel of the stream
+    pdl_wait();
+    if (*p.stop_flag) return;                // uniform across the grid
+  }
   const uint32_t cta_rank = CG == 2 ? umma::cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const int n_workers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;    // CTAs (or CTA pairs)
@@ -414,6 +437,10 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (CG == 2) umma::cluster_sync();       // peer barriers are initialised before anything signals them
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, bias = a weight) overlapped
+  // the tail of the previous kernel in the stream; from here on its outputs are read and its inputs overwritten
+  pdl_wait();
+  pdl_launch_dependents();
 
   // tile decode: n-tile fastest so CTAs that run concurrently share A tiles in L2
   // (for CG == 2 `t` indexes pairs of M tiles; this CTA takes M tile 2*pair + rank)
@@ -510,16 +537,19 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (CG == 2) umma::mma_commit_2cta(bar);
         else umma::mma_commit(bar);
       };
-      uint32_t git = 0, gch = 0, tcount = 0, ts_slot = 0;
+      uint32_t git = 0, gch = 0, tcount = 0;
       if (WR > 0) { umma::mbar_wait(bres_bar, 0); umma::tc_fence_after(); }
       const uint32_t bres_addr = umma::smem_u32(smem + C::kBResOffset);
       for (int tile = worker; tile < total_work; tile += n_workers, ++tcount) {
         const uint32_t xb = C::kCrossBufs == 2 ? (tcount & 1) : 0u;
         const uint32_t tmem_cross = tmem_base + (2 + xb) * BN;
+        long long* trace = (p.dbg && tcount < 32) ? p.dbg + ((size_t)blockIdx.x * 32 + tcount) * 8 : nullptr;
+        if (trace && lane == 0) trace[0] = clock64();
         if (P == 2) {   // the epilogue must have read this cross accumulator's previous use
           umma::mbar_wait(&cross_empty_bar[xb], (C::kCrossBufs == 2 ? ((tcount >> 1) & 1) : (tcount & 1)) ^ 1);
           umma::tc_fence_after();
         }
+        if (trace && lane == 0) trace[1] = clock64();
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk, ++gch) {
           const int buf = gch & 1;
@@ -552,27 +582,6 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int k = 0; k < kConvBK / 16; ++k) {
                 const uint64_t koff = (uint64_t)(k * 32 >> 4);  // 16 elements = 32 bytes along K
-                if (P == 2 && p.a_tmem) {
-                  // A slices through tensor memory: a_hi is read from shared memory once for its two products
-                  // (SS MMAs read 18 KB of operands per k-step and SM, this form 14 KB -- the shared-memory
-                  // bandwidth is what bounds these MMAs, profiles/r01_enc1_smem_bandwidth.txt)
-                  const uint32_t ta = tmem_base + C::kStageCol + (ts_slot & 7u) * 16u;
-                  ++ts_slot;
-                  if (CG == 2) {
-                    umma::tmem_cp_128x256b_2cta(ta, a_hi + koff);
-                    umma::tmem_cp_128x256b_2cta(ta + 8, a_lo + koff);
-                    umma::mma_f16_ts_2cta(tmem_main, ta, b_hi + koff, idesc, (it != it_begin || kx != 0 || k != 0) ? 1u : 0u);
-                    umma::mma_f16_ts_2cta(tmem_cross, ta, b_lo + koff, idesc, (it | kx | k) != 0 ? 1u : 0u);
-                    umma::mma_f16_ts_2cta(tmem_cross, ta + 8, b_hi + koff, idesc, 1u);
-                  } else {
-                    umma::tmem_cp_128x256b(ta, a_hi + koff);
-                    umma::tmem_cp_128x256b(ta + 8, a_lo + koff);
-                    umma::mma_f16_ts(tmem_main, ta, b_hi + koff, idesc, (it != it_begin || kx != 0 || k != 0) ? 1u : 0u);
-                    umma::mma_f16_ts(tmem_cross, ta, b_lo + koff, idesc, (it | kx | k) != 0 ? 1u : 0u);
-                    umma::mma_f16_ts(tmem_cross, ta + 8, b_hi + koff, idesc, 1u);
-                  }
-                  continue;
-                }
                 mma(tmem_main, a_hi + koff, b_hi + koff, idesc, (it != it_begin || kx != 0 || k != 0) ? 1u : 0u);
                 if (P == 2) {   // hi*lo + lo*hi (lo*lo ~ 2^-22 relative is dropped)
                   mma(tmem_cross, a_hi + koff, b_lo + koff, idesc, (it | kx | k) != 0 ? 1u : 0u);
@@ -586,6 +595,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (umma::elect_one()) commit(&acc_full_bar[buf]);  // this chunk's accumulator (and all earlier MMAs) done
           __syncwarp();
+          if (trace && lane == 0) trace[2 + (chunk == n_chunks - 1 ? 1 : 0)] = clock64();   // [2] first chunk issued, [3] all issued
         }
       }
     }
@@ -608,24 +618,20 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       float acc[kHalf];
 #pragma unroll
       for (int j = 0; j < kHalf; ++j) acc[j] = 0.f;
+      long long* trace = (p.dbg && tcount < 32 && warp == 2) ? p.dbg + ((size_t)blockIdx.x * 32 + tcount) * 8 : nullptr;
+      if (trace && lane == 0) trace[4] = clock64();                     // epilogue ready for this tile
       for (int chunk = 0; chunk < n_chunks; ++chunk, ++gch) {
         const int buf = gch & 1;
         umma::mbar_wait(&acc_full_bar[buf], (gch >> 1) & 1);
         umma::tc_fence_after();
-        auto drain = [&](uint32_t col0) {   // acc += TMEM[col0 .. col0 + kHalf): two 16-column loads in flight per wait
+        if (trace && lane == 0 && chunk == n_chunks - 1) trace[5] = clock64();   // last chunk's MMAs complete
+        auto drain = [&](uint32_t col0) {   // acc += TMEM[col0 .. col0 + kHalf): every 16-column load in flight before ONE wait
+          uint32_t r[kHalf];                // (a wait per pair of loads cost ~700 cycles each: 2900 cycles for the final drain of a 128-wide tile)
 #pragma unroll
-          for (int gi = 0; gi < kGroups; gi += 2) {
-            uint32_t r0[16], r1[16];
-            umma::tmem_ld_32x16(tmem_base + lane_col + col0 + (uint32_t)(gi * 16), r0);
-            if (gi + 1 < kGroups) umma::tmem_ld_32x16(tmem_base + lane_col + col0 + (uint32_t)(gi * 16 + 16), r1);
-            umma::tmem_ld_wait();
+          for (int gi = 0; gi < kGroups; ++gi) umma::tmem_ld_32x16(tmem_base + lane_col + col0 + (uint32_t)(gi * 16), r + gi * 16);
+          umma::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[gi * 16 + j] += __uint_as_float(r0[j]);
-            if (gi + 1 < kGroups) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) acc[gi * 16 + 16 + j] += __uint_as_float(r1[j]);
-            }
-          }
+          for (int j = 0; j < kHalf; ++j) acc[j] += __uint_as_float(r[j]);
         };
         drain((uint32_t)(buf * BN));
         const uint32_t xb = C::kCrossBufs == 2 ? (tcount & 1) : 0u;
@@ -642,6 +648,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      if (trace && lane == 0) trace[6] = clock64();                     // accumulators drained
       // ---- bias / activation / store (overlaps the next tile's main loop).  The activation is dispatched
       // ONCE per tile to a specialised instance: a per-element runtime select made the compiler evaluate
       // erff, expf, tanhf ... for every output (measured: ~9000 instructions per warp per tile).
@@ -651,6 +658,10 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const float* bias = p.bias ? p.bias + n0 + half * kHalf : nullptr;
       if (p.act < 5 && p.Cout <= C::kMaxBias) {
         const float* bias_s = bias_smem + n0 + half * kHalf;
+        if (p.border_bias) {
+          const int yc = py == 0 ? 0 : (py == p.H_out - 1 ? 2 : 1), xc = px == 0 ? 0 : (px == p.W_out - 1 ? 2 : 1);
+          if (yc != 1 || xc != 1) bias_s = p.border_bias + (size_t)(yc * 3 + xc) * p.Cout + n0 + half * kHalf;
+        }
         switch (p.act) {
           case 0: conv_epilogue_fast<0, kHalf>(acc, p, pix, ch0, bias_s); break;
           case 1: conv_epilogue_fast<1, kHalf>(acc, p, pix, ch0, bias_s); break;
@@ -658,6 +669,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           case 3: conv_epilogue_fast<3, kHalf>(acc, p, pix, ch0, bias_s); break;
           default: conv_epilogue_fast<4, kHalf>(acc, p, pix, ch0, bias_s); break;
         }
+        if (trace && lane == 0) trace[7] = clock64();                   // tile stored
         continue;
       }
       switch (p.act) {
@@ -730,6 +742,8 @@ k_conv_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   umma::cluster_sync();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
   const int m_tiles = p.tiles_x * p.tiles_y;
   const int total_work = (m_tiles >> 1) * p.n_groups;
   auto decode = [&](int t, int& g, int& x0, int& y0) {
@@ -842,6 +856,217 @@ k_conv_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) umma::tmem_dealloc_2cta(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------ two output rows per CTA (decoder-half 3x3 layers)
+// k_conv_rows2: 3x3 stride-1 convolution, split planes, BN = 96, rows of >= 256 pixels.  A CTA pair computes TWO output
+// rows x 256 pixels x 96 channels.  Why: with one output row per CTA the u4/u5 layers are bound by the rate at which an
+// SM ingests operands from L2 (~28 B/cycle/SM, profiles/r01_conv_fill_rate_model.txt): per 32-channel chunk a CTA
+// loads 3 haloed activation rows + the 9 weight taps for 54 MMAs (35-40 B per MMA cycle).  Two output rows share
+// their activation rows (4 haloed rows instead of 6) and every weight tap (loaded once for both rows), so the same
+// chunk costs 4 rows + 9 taps for 108 MMAs: ~20 B per MMA cycle, below the fill rate -- the tensor pipe becomes the bound.
+// Pipeline item = (chunk kc, activation row a in 0..3): TMA lands haloed row a (130 px x 32 ch x 2 planes) and, for
+// a < 3, the three kx taps of kernel row ky = a (both planes, this CTA's half of the 96 weight rows).  Item a feeds
+// output row 0 with ky = a and output row 1 with ky = a - 1, so the weights of item a-1 are used once more: a slot
+// is released one item late.  TMEM: main and cross accumulators of both rows (4 x 96 columns); the hi*hi chain is
+// NOT cut here (K/16 <= 256 MMAs per chain is enforced by the host; the layers that use this kernel have 54-216),
+// so the epilogue is a single drain per row followed by bias / activation / split / store.
+constexpr int kR2BN = 96;
+constexpr int kR2ABytes = 136 * kConvRowB;                 // one haloed row, one plane (TMA writes 130 rows)
+constexpr int kR2ATx = 130 * kConvRowB;
+constexpr int kR2BBytes = (kR2BN / 2) * kConvRowB;         // one tap, one plane, this CTA's 48 weight rows
+constexpr int kR2StageBytes = 2 * kR2ABytes + 6 * kR2BBytes;   // 17408 + 18432
+constexpr int kR2Stages = 6;
+constexpr int kR2BarOffset = kR2Stages * kR2StageBytes;    // 215040
+constexpr int kR2BiasOffset = kR2BarOffset + 256;
+constexpr int kR2MaxBias = 1024;
+constexpr int kR2Total = kR2BiasOffset + kR2MaxBias * 4 + 1024;
+
+template <int ACT>
+__device__ __forceinline__ void rows2_store(const float* acc, const ConvParams& p, int py, int px, long long ch0,
+                                            const float* bias_smem, int nofs) {
+  const long long pix = (long long)py * p.W_out + px;
+  const float* bias_s = bias_smem + nofs;
+  if (p.border_bias) {
+    const int yc = py == 0 ? 0 : (py == p.H_out - 1 ? 2 : 1), xc = px == 0 ? 0 : (px == p.W_out - 1 ? 2 : 1);
+    if (yc != 1 || xc != 1) bias_s = p.border_bias + (size_t)(yc * 3 + xc) * p.Cout + nofs;
+  }
+  conv_epilogue_fast<ACT, kR2BN / 2>(acc, p, pix, ch0, bias_s);
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+k_conv_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + kR2BarOffset);
+  uint64_t* empty_bar = full_bar + kR2Stages;
+  uint64_t* acc_full_bar = empty_bar + kR2Stages;     // [2] one per output row
+  uint64_t* acc_empty_bar = acc_full_bar + 2;         // [2]
+  uint32_t* tmem_ptr_smem = (uint32_t*)(acc_empty_bar + 2);
+  float* bias_smem = (float*)(smem + kR2BiasOffset);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = umma::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int n_workers = (int)(gridDim.x >> 1), worker = (int)(blockIdx.x >> 1);
+  const int KC = p.k_chunks;
+  if (warp == 0 && lane == 0) {
+    umma::tma_prefetch_desc(&tmA);
+    umma::tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kR2Stages; ++s) { umma::mbar_init(&full_bar[s], 1); umma::mbar_init(&empty_bar[s], 1); }
+    for (int r = 0; r < 2; ++r) { umma::mbar_init(&acc_full_bar[r], 1); umma::mbar_init(&acc_empty_bar[r], kConvEpiWarps * 2); }
+    umma::fence_barrier_init();
+  } else if (warp == 1) {
+    umma::tmem_alloc_2cta(tmem_ptr_smem, 512);
+  }
+  for (int i = threadIdx.x; i < p.Cout && i < kR2MaxBias; i += kConvThreads) bias_smem[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  // pair tile t: n-tile fastest (pairs that run concurrently share activation rows in L2), then pair column, then row pair
+  const int pair_cols = p.W_out >> 8;
+  const int total_work = pair_cols * (p.H_out >> 1) * p.n_tiles_n;
+  auto decode = [&](int t, int& x0, int& y0, int& n0) {
+    const int nt = t % p.n_tiles_n; t /= p.n_tiles_n;
+    const int pc = t % pair_cols;
+    x0 = (pc * 2 + (int)cta_rank) * 128; y0 = (t / pair_cols) * 2; n0 = nt * kR2BN;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    uint32_t git = 0;
+    for (int tile = worker; tile < total_work; tile += n_workers) {
+      int x0, y0, n0;
+      decode(tile, x0, y0, n0);
+      const int nb0 = n0 + (int)cta_rank * (kR2BN / 2);
+      for (int kc = 0; kc < KC; ++kc) {
+        for (int a = 0; a < 4; ++a, ++git) {
+          const int s = git % kR2Stages;
+          umma::mbar_wait(&empty_bar[s], ((git / kR2Stages) & 1) ^ 1);
+          const uint32_t fb = umma::mapa_u32(umma::smem_u32(&full_bar[s]), 0);
+          uint8_t* a_dst = smem + s * kR2StageBytes;
+          uint8_t* b_dst = a_dst + 2 * kR2ABytes;
+          if (umma::elect_one()) {
+            if (leader) umma::mbar_arrive_expect_tx(&full_bar[s], 2u * (2u * kR2ATx + (a < 3 ? 6u * kR2BBytes : 0u)));
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+              umma::tma_load_4d_2cta(a_dst + pl * kR2ABytes, &tmA, fb, p.cin_off + kc * kConvBK, x0 - 1, y0 + a - 1, pl);
+            if (a < 3) {
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl)
+                  umma::tma_load_3d_2cta(b_dst + (kx * 2 + pl) * kR2BBytes, &tmB, fb, (a * 3 + kx) * p.Cin + kc * kConvBK, nb0, pl);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = umma::idesc_f16kind_f32(256, kR2BN, 0u, 0u);
+      uint32_t git = 0, tcount = 0;
+      for (int tile = worker; tile < total_work; tile += n_workers, ++tcount) {
+        for (int kc = 0; kc < KC; ++kc) {
+          for (int a = 0; a < 4; ++a, ++git) {
+            const int s = git % kR2Stages;
+            if (kc == 0 && a < 2) {   // first MMAs into output row `a` of this tile: the epilogue has drained the previous tile's
+              umma::mbar_wait(&acc_empty_bar[a], (tcount & 1) ^ 1);
+              umma::tc_fence_after();
+            }
+            umma::mbar_wait(&full_bar[s], (git / kR2Stages) & 1);
+            umma::tc_fence_after();
+            const uint32_t a_addr = umma::smem_u32(smem + s * kR2StageBytes);
+            if (umma::elect_one()) {
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                const int ky = a - r;
+                if (ky < 0 || ky > 2) continue;
+                // weights of kernel row ky live in the slot of item (kc, ky) = git - a + ky
+                const uint32_t b_addr = umma::smem_u32(smem + ((git - (uint32_t)a + (uint32_t)ky) % kR2Stages) * kR2StageBytes) + 2 * kR2ABytes;
+                const uint32_t t_main = tmem_base + (uint32_t)(r * kR2BN), t_cross = tmem_base + (uint32_t)((2 + r) * kR2BN);
+                const bool first = kc == 0 && ky == 0;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                  const uint64_t a_hi = umma::smem_desc_kmajor<kConvRowB>(a_addr + kx * kConvRowB);
+                  const uint64_t a_lo = umma::smem_desc_kmajor<kConvRowB>(a_addr + kR2ABytes + kx * kConvRowB);
+                  const uint64_t b_hi = umma::smem_desc_kmajor<kConvRowB>(b_addr + (kx * 2) * kR2BBytes);
+                  const uint64_t b_lo = umma::smem_desc_kmajor<kConvRowB>(b_addr + (kx * 2 + 1) * kR2BBytes);
+#pragma unroll
+                  for (int k = 0; k < kConvBK / 16; ++k) {
+                    const uint64_t koff = (uint64_t)(k * 32 >> 4);
+                    const uint32_t acc = (first && kx == 0 && k == 0) ? 0u : 1u;
+                    umma::mma_bf16_ss_2cta(t_main, a_hi + koff, b_hi + koff, idesc, acc);
+                    umma::mma_bf16_ss_2cta(t_cross, a_hi + koff, b_lo + koff, idesc, acc);
+                    umma::mma_bf16_ss_2cta(t_cross, a_lo + koff, b_hi + koff, idesc, 1u);
+                  }
+                }
+              }
+              // item a-1 (its weights were used once more just now) and, at the end of a chunk, item 3 are free
+              if (a >= 1) umma::mma_commit_2cta(&empty_bar[(git - 1) % kR2Stages]);
+              if (a == 3) umma::mma_commit_2cta(&empty_bar[s]);
+              if (kc == KC - 1 && a >= 2) umma::mma_commit_2cta(&acc_full_bar[a - 2]);   // row 0 ends with item 2, row 1 with item 3
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: drain both rows, release TMEM, then bias / activation / split / store =====================
+    const int q = warp & 3, half = (warp - 2) >> 2, row = q * 32 + lane;
+    constexpr int kHalf = kR2BN / 2;
+    const uint32_t lane_col = ((uint32_t)(q * 32) << 16) + (uint32_t)(half * kHalf);
+    const uint32_t ae0 = umma::mapa_u32(umma::smem_u32(&acc_empty_bar[0]), 0);
+    const uint32_t ae1 = umma::mapa_u32(umma::smem_u32(&acc_empty_bar[1]), 0);
+    uint32_t tcount = 0;
+    for (int tile = worker; tile < total_work; tile += n_workers, ++tcount) {
+      int x0, y0, n0;
+      decode(tile, x0, y0, n0);
+      float acc[2][kHalf];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        umma::mbar_wait(&acc_full_bar[r], tcount & 1);
+        umma::tc_fence_after();
+#pragma unroll
+        for (int gi = 0; gi < kHalf / 16; ++gi) {
+          uint32_t m[16], c[16];
+          umma::tmem_ld_32x16(tmem_base + lane_col + (uint32_t)(r * kR2BN + gi * 16), m);
+          umma::tmem_ld_32x16(tmem_base + lane_col + (uint32_t)((2 + r) * kR2BN + gi * 16), c);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[r][gi * 16 + j] = __uint_as_float(m[j]) + __uint_as_float(c[j]);
+        }
+        umma::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive_cluster(r ? ae1 : ae0);
+      }
+      const int px = x0 + row;
+      const long long ch0 = (long long)p.cout_off + n0 + half * kHalf;
+      const int nofs = n0 + half * kHalf;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        switch (p.act) {
+          case 0: rows2_store<0>(acc[r], p, y0 + r, px, ch0, bias_smem, nofs); break;
+          case 1: rows2_store<1>(acc[r], p, y0 + r, px, ch0, bias_smem, nofs); break;
+          case 2: rows2_store<2>(acc[r], p, y0 + r, px, ch0, bias_smem, nofs); break;
+          case 3: rows2_store<3>(acc[r], p, y0 + r, px, ch0, bias_smem, nofs); break;
+          default: rows2_store<4>(acc[r], p, y0 + r, px, ch0, bias_smem, nofs); break;
+        }
+      }
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync();
+  if (warp == 1) umma::tmem_dealloc_2cta(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------ bilinear 2x upsample
 // nn.functional.interpolate(scale_factor=2, mode="bilinear", align_corners=False) of
 // BilinearDecoder (unet.py:7-16) on an NHWC plane tensor; writes a channel slice of the
@@ -853,6 +1078,8 @@ k_upsample2x(const __nv_bfloat16* __restrict__ in, int in_planes, long long in_p
              int Cout_total, int cout_off) {
   const int c8 = c / 8;
   const long long total = (long long)(2 * h) * (2 * w) * c8;
+  pdl_wait();
+  pdl_launch_dependents();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cc = (int)(i % c8) * 8;
@@ -927,7 +1154,9 @@ static int g_weights_resident = 1;
 static int g_wide_tiles = 1;
 static int g_pair_min_mmas = 48;
 static int g_max_sms = kNumSMs;   // experiment knob: SMs a persistent launch may occupy
-static int g_a_tmem = 0;   // measured neutral on the 128-wide layers, slower on the 64-wide ones (profiles/r01_conv_a_tmem_ab.txt)
+static long long* g_dbg = nullptr;
+static int g_rows2 = 1;    // two output rows per CTA pair for the 96-channel decoder-half layers (k_conv_rows2)
+static int g_pdl = 1;      // programmatic dependent launch between the backbone's kernels
 
 template <int BN, int P, int NX, int CG, int WR = 0>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
@@ -946,10 +1175,12 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   grid *= CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = C::kTotal; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
   HIMO_CUDA_RET(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   HIMO_LAUNCH_RET();
   return HIMO_OK;
@@ -965,8 +1196,10 @@ static int g_disable_halo = 0;
 extern "C" int himo_conv_set_halo(int enable) { g_disable_halo = enable ? 0 : 1; return HIMO_OK; }
 // A/B knob: 0 disables the CTA-pair (cta_group::2) path.
 extern "C" int himo_conv_set_2cta(int enable) { g_enable_2cta = enable ? 1 : 0; return HIMO_OK; }
-// A/B knob: 0 reads both MMA operands from shared memory (SS form) instead of staging A in tensor memory.
-extern "C" int himo_conv_set_a_tmem(int enable) { g_a_tmem = enable ? 1 : 0; return HIMO_OK; }
+// Retired experiment (round 1: the A operand staged in tensor memory, tcgen05.cp + TS-form MMAs -- bit-identical, neutral to
+// slower, profiles/r01_conv_a_tmem_ab.txt).  Its 128 staging columns now hold the second cross accumulator of the 128-wide
+// tiles; the entry point stays so that existing callers keep linking.
+extern "C" int himo_conv_set_a_tmem(int) { return HIMO_OK; }
 // Experiment knob: number of SMs a persistent convolution launch occupies (default all 148); used to tell a per-SM
 // operand-fill limit from a chip-wide one.
 extern "C" int himo_conv_set_max_sms(int n) { g_max_sms = n < 2 ? 2 : (n > kNumSMs ? kNumSMs : n); return HIMO_OK; }
@@ -976,6 +1209,12 @@ extern "C" int himo_conv_set_pair_min_mmas(int n) { g_pair_min_mmas = n; return 
 extern "C" int himo_conv_set_wide_tiles(int enable) { g_wide_tiles = enable ? 1 : 0; return HIMO_OK; }
 // A/B knob: 0 disables the weights-resident variants of the 64-channel encoder layers.
 extern "C" int himo_conv_set_weights_resident(int enable) { g_weights_resident = enable ? 1 : 0; return HIMO_OK; }
+// Profiling hook: device buffer of [grid][32][8] int64 that k_conv_umma fills with clock64() marks per tile (NULL = off).
+extern "C" int himo_conv_set_debug_buffer(void* buf) { g_dbg = (long long*)buf; return HIMO_OK; }
+// A/B knob: 0 disables the two-output-rows tiles (k_conv_rows2) of the 96-channel decoder-half layers.
+extern "C" int himo_conv_set_rows2(int enable) { g_rows2 = enable ? 1 : 0; return HIMO_OK; }
+// A/B knob: 0 launches the backbone kernels without programmatic dependent launch (full stream serialisation).
+extern "C" int himo_conv_set_pdl(int enable) { g_pdl = enable ? 1 : 0; return HIMO_OK; }
 // A/B knob: 0 launches one CTA per tile instead of the persistent one-CTA-per-SM tile loop.
 extern "C" int himo_conv_set_persistent(int enable) { g_persistent = enable ? 1 : 0; return HIMO_OK; }
 // Tuning knob (process-wide): number of hi*hi MMAs (K = 16 each) accumulated in tensor memory before the
@@ -1062,7 +1301,6 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
     const int per_stage = 2 * (halo ? 3 : 1);
     p.flush_stages = g_flush_mmas / per_stage > 0 ? g_flush_mmas / per_stage : 1;
   }
-  p.a_tmem = g_a_tmem;
   p.out_t = (__nv_bfloat16*)d->out_t; p.out_t_plane_stride = d->out_t_plane_stride; p.ld_t = d->ld_t;
   p.mask_src = (const __nv_bfloat16*)d->mask_src; p.mask_plane_stride = d->mask_plane_stride;
   p.mask_planes = d->mask_planes;
@@ -1070,10 +1308,37 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
   p.stop_flag = d->stop_flag;
   p.aux_h = d->aux_h; p.aux_z = d->aux_z; p.aux_ld = d->aux_ld;
   p.out2 = (__nv_bfloat16*)d->out2; p.out2_plane_stride = d->out2_plane_stride; p.out2_ld = d->out2_ld;
+  p.border_bias = d->border_bias; p.H_out = H_out; p.dbg = g_dbg;
+  if (d->border_bias && (d->act >= 5 || d->Cout > 1024)) return HIMO_ERR_UNSUPPORTED;
   p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles_n * groups;
+  // two output rows per CTA pair for the decoder-half 3x3 layers with 96-channel N tiles (k_conv_rows2)
+  if (g_rows2 && P == 2 && halo && BN == 96 && W_out % 256 == 0 && H_out % 2 == 0 && groups == 1 && d->act < 5 &&
+      d->Cout <= kR2MaxBias && !d->out_t && !d->mask_src && !d->stop_flag && d->b_group_k_stride == 0 && !d->b_k_total &&
+      taps * p.k_chunks * 2 <= 256 && CGsel == 2) {
+    static bool r2_configured_dev[64] = {};
+    int dev_ = 0;
+    HIMO_CUDA_RET(cudaGetDevice(&dev_));
+    if (!r2_configured_dev[dev_ & 63]) {
+      HIMO_CUDA_RET(cudaFuncSetAttribute(k_conv_rows2, cudaFuncAttributeMaxDynamicSharedMemorySize, kR2Total));
+      r2_configured_dev[dev_ & 63] = true;
+    }
+    const int work = (W_out / 256) * (H_out / 2) * p.n_tiles_n;
+    const int pairs = work < g_max_sms / 2 ? work : g_max_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pairs * 2); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = kR2Total; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
+    HIMO_CUDA_RET(cudaLaunchKernelEx(&cfg, k_conv_rows2, tmA, tmB, p));
+    HIMO_LAUNCH_RET();
+    return HIMO_OK;
+  }
   // 256-channel layers on short rows: one 256-wide N tile per CTA pair (k_conv_wide)
   if (g_wide_tiles && P == 2 && d->Cout == 256 && d->Cin % kWideBK == 0 && !halo && m_tiles_total % 2 == 0 && (d->act == 0 || d->act == 1) &&
-      !d->out_t && !d->mask_src && !d->stop_flag && d->b_group_k_stride == 0 && !d->b_k_total) {
+      !d->out_t && !d->mask_src && !d->stop_flag && d->b_group_k_stride == 0 && !d->b_k_total && !d->border_bias) {
     CUtensorMap tmBw, tmAw;
     cuuint64_t dimsw[3] = {(cuuint64_t)k_total, (cuuint64_t)d->Cout, 2};
     cuuint64_t stridesw[2] = {(cuuint64_t)k_total * 2, (cuuint64_t)d->Cout * k_total * 2};
@@ -1106,10 +1371,12 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
     const int pairs = work < kNumSMs / 2 ? work : kNumSMs / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pairs * 2); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = kWideTotal; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
     HIMO_CUDA_RET(cudaLaunchKernelEx(&cfg, k_conv_wide, tmAw, tmBw, p));
     HIMO_LAUNCH_RET();
     return HIMO_OK;
@@ -1142,9 +1409,14 @@ extern "C" int himo_upsample2x_nhwc(const void* in, int in_planes, long long in_
   cudaStream_t stream = (cudaStream_t)stream_;
   const long long total = (long long)(2 * h) * (2 * w) * (c / 8);
   const int blocks = (int)((total + 255) / 256 < (long long)kNumSMs * 16 ? (total + 255) / 256 : kNumSMs * 16);
-  k_upsample2x<<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)in, in_planes, in_plane_stride, h, w, c,
-                                           (__nv_bfloat16*)out, out_planes, out_plane_stride, Cout_total,
-                                           cout_off);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+  HIMO_CUDA_RET(cudaLaunchKernelEx(&cfg, k_upsample2x, (const __nv_bfloat16*)in, in_planes, in_plane_stride, h, w, c,
+                                   (__nv_bfloat16*)out, out_planes, out_plane_stride, Cout_total, cout_off));
   HIMO_LAUNCH_RET();
   return HIMO_OK;
 }

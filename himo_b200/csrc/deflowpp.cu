@@ -60,7 +60,7 @@ static size_t net_layout(int n_max, int planes, const float* vs, const float* cr
 
 static int conv(const Act& in, int cin_off, int cin, int groups, const void* w, const float* bias, int cout,
                 int ksize, int stride, int act, const Act& out, int cout_off, int planes, cudaStream_t stream,
-                float acc_scale, float* out_f32 = nullptr) {
+                float acc_scale, float* out_f32 = nullptr, const float* border_bias = nullptr) {
   himo_conv_desc d = {};
   d.in = in.p; d.in_planes = planes; d.in_plane_stride = in.plane_stride();
   d.H_in = in.H; d.W_in = in.W; d.Cin_total = in.C; d.cin_off = cin_off; d.Cin = cin;
@@ -69,6 +69,7 @@ static int conv(const Act& in, int cin_off, int cin, int groups, const void* w, 
   else { d.out = out.p; d.out_fp32 = 0; d.out_planes = planes; d.out_plane_stride = out.plane_stride(); d.Cout_total = out.C; }
   d.cout_off = cout_off; d.act = act; d.acc_scale = acc_scale;
   d.n_groups = groups; d.cin_group_stride = groups > 1 ? cin : 0; d.cout_group_stride = groups > 1 ? cout : 0;
+  d.border_bias = border_bias;
   return himo_conv2d_nhwc(&d, stream);
 }
 
@@ -129,41 +130,51 @@ extern "C" int himo_deflowpp_forward(const himo_deflowpp_weights* w, const himo_
   const double crd[6] = {-51.2, -51.2, -3.0, 51.2, 51.2, 3.0};
   for (int k = 0; k < 6; ++k) e.coors_range_f64[k] = crd[k];
   e.pfn_weight = w->pfn_w; e.pfn_bias = w->pfn_b;
-  e.canvas = nb.B.p; e.canvas_planes = P; e.skip_canvas_clear = 0;
+  // composed u3 -> u4 (himo_deflowpp_weights::dec_bb): the skip tensors are consumed by u4 directly, so every skip
+  // producer writes into the second half of its block's concatenation buffer and the three u3 launches disappear
+  const bool composed = w->dec_bb[0] && w->dec_bb[1] && w->dec_bb[2];
+  e.canvas_planes = P; e.skip_canvas_clear = 0;
+  if (composed) { e.canvas = nb.CAT3.p; e.canvas_ld = nb.CAT3.C; e.canvas_ch_off = 96; }
+  else { e.canvas = nb.B.p; e.canvas_ld = 0; e.canvas_ch_off = 0; }
   e.workspace = nb.embed_ws; e.workspace_bytes = nb.embed_ws_bytes;
   HIMO_RET(himo_embed_frames(&e, stream));
 
   mark(1);
   // ---- shared encoder on the three pseudo-images (unet.py:139-150), frames = conv groups
   int li = 0;
-  auto enc = [&](const Act& in, int cin, const Act& out, int cout, int stride) {
-    int s = conv(in, 0, cin, 3, w->enc_w[li], w->enc_b[li], cout, 3, stride, 1, out, 0, P, stream, w->enc_s[li]);
+  auto enc = [&](const Act& in, int cin_off, int cin, const Act& out, int cout_off, int cout, int stride) {
+    int s = conv(in, cin_off, cin, 3, w->enc_w[li], w->enc_b[li], cout, 3, stride, 1, out, cout_off, P, stream, w->enc_s[li]);
     ++li;
     return s;
   };
-  HIMO_RET(enc(nb.B, 32, nb.Fa, 64, 2));
-  HIMO_RET(enc(nb.Fa, 64, nb.Fb, 64, 1)); HIMO_RET(enc(nb.Fb, 64, nb.Fa, 64, 1)); HIMO_RET(enc(nb.Fa, 64, nb.Fb, 64, 1));
-  HIMO_RET(enc(nb.Fb, 64, nb.La, 128, 2));
-  HIMO_RET(enc(nb.La, 128, nb.Lb, 128, 1)); HIMO_RET(enc(nb.Lb, 128, nb.La, 128, 1)); HIMO_RET(enc(nb.La, 128, nb.Lb, 128, 1));
-  HIMO_RET(enc(nb.Lb, 128, nb.La, 128, 1)); HIMO_RET(enc(nb.La, 128, nb.Lb, 128, 1));
-  HIMO_RET(enc(nb.Lb, 128, nb.Ra, 256, 2));
-  HIMO_RET(enc(nb.Ra, 256, nb.Rb, 256, 1)); HIMO_RET(enc(nb.Rb, 256, nb.Ra, 256, 1)); HIMO_RET(enc(nb.Ra, 256, nb.Rb, 256, 1));
-  HIMO_RET(enc(nb.Rb, 256, nb.Ra, 256, 1)); HIMO_RET(enc(nb.Ra, 256, nb.Rb, 256, 1));
-  // Fstar = Fb [256^2,192], Lstar = Lb [128^2,384], Rstar = Rb [64^2,768], Bstar = B [512^2,96]
+  // skip tensors: Bstar [512^2,96] (canvas), Fstar [256^2,192], Lstar [128^2,384], Rstar = Rb [64^2,768]
+  const Act& Bs = composed ? nb.CAT3 : nb.B;   const int b_off = composed ? 96 : 0;
+  const Act& Fs = composed ? nb.CAT2 : nb.Fb;  const int f_off = composed ? 192 : 0;
+  const Act& Ls = composed ? nb.CAT1 : nb.Lb;  const int l_off = composed ? 384 : 0;
+  HIMO_RET(enc(Bs, b_off, 32, nb.Fa, 0, 64, 2));
+  HIMO_RET(enc(nb.Fa, 0, 64, nb.Fb, 0, 64, 1)); HIMO_RET(enc(nb.Fb, 0, 64, nb.Fa, 0, 64, 1)); HIMO_RET(enc(nb.Fa, 0, 64, Fs, f_off, 64, 1));
+  HIMO_RET(enc(Fs, f_off, 64, nb.La, 0, 128, 2));
+  HIMO_RET(enc(nb.La, 0, 128, nb.Lb, 0, 128, 1)); HIMO_RET(enc(nb.Lb, 0, 128, nb.La, 0, 128, 1)); HIMO_RET(enc(nb.La, 0, 128, nb.Lb, 0, 128, 1));
+  HIMO_RET(enc(nb.Lb, 0, 128, nb.La, 0, 128, 1)); HIMO_RET(enc(nb.La, 0, 128, Ls, l_off, 128, 1));
+  HIMO_RET(enc(Ls, l_off, 128, nb.Ra, 0, 256, 2));
+  HIMO_RET(enc(nb.Ra, 0, 256, nb.Rb, 0, 256, 1)); HIMO_RET(enc(nb.Rb, 0, 256, nb.Ra, 0, 256, 1)); HIMO_RET(enc(nb.Ra, 0, 256, nb.Rb, 0, 256, 1));
+  HIMO_RET(enc(nb.Rb, 0, 256, nb.Ra, 0, 256, 1)); HIMO_RET(enc(nb.Ra, 0, 256, nb.Rb, 0, 256, 1));
 
   // ---- UpsampleSkip x3 (unet.py:31-35) + decoder_step4
-  auto up_block = [&](int bi, const Act& a, const Act& skip, int latent, int out_c, const Act& T, const Act& CAT,
-                      const Act& X, const Act& Y) {
+  auto up_block = [&](int bi, const Act& a, const Act& skip, int skip_off, int latent, int out_c, const Act& T,
+                      const Act& CAT, const Act& X, const Act& Y) {
     HIMO_RET(conv(a, 0, a.C, 1, w->dec_w[bi][0], w->dec_b[bi][0], latent, 1, 1, 0, T, 0, P, stream, w->dec_s[bi][0]));
     HIMO_RET(himo_upsample2x_nhwc(T.p, P, T.plane_stride(), T.H, T.W, latent, CAT.p, P, CAT.plane_stride(), CAT.C, 0, stream));
-    HIMO_RET(conv(skip, 0, skip.C, 1, w->dec_w[bi][1], w->dec_b[bi][1], latent, 1, 1, 0, CAT, latent, P, stream, w->dec_s[bi][1]));
-    HIMO_RET(conv(CAT, 0, CAT.C, 1, w->dec_w[bi][2], w->dec_b[bi][2], out_c, 3, 1, 0, X, 0, P, stream, w->dec_s[bi][2]));
+    if (!composed)
+      HIMO_RET(conv(skip, skip_off, latent, 1, w->dec_w[bi][1], w->dec_b[bi][1], latent, 1, 1, 0, CAT, latent, P, stream, w->dec_s[bi][1]));
+    HIMO_RET(conv(CAT, 0, CAT.C, 1, w->dec_w[bi][2], w->dec_b[bi][2], out_c, 3, 1, 0, X, 0, P, stream, w->dec_s[bi][2],
+                  nullptr, composed ? w->dec_bb[bi] : nullptr));
     HIMO_RET(conv(X, 0, X.C, 1, w->dec_w[bi][3], w->dec_b[bi][3], out_c, 3, 1, 0, Y, 0, P, stream, w->dec_s[bi][3]));
     return HIMO_OK;
   };
-  HIMO_RET(up_block(0, nb.Rb, nb.Lb, 384, 384, nb.T1, nb.CAT1, nb.La, nb.S));
-  HIMO_RET(up_block(1, nb.S, nb.Fb, 192, 192, nb.T2, nb.CAT2, nb.Fa, nb.Tt));
-  HIMO_RET(up_block(2, nb.Tt, nb.B, 96, 96, nb.T3, nb.CAT3, nb.X3, nb.U));
+  HIMO_RET(up_block(0, nb.Rb, Ls, l_off, 384, 384, nb.T1, nb.CAT1, nb.La, nb.S));
+  HIMO_RET(up_block(1, nb.S, Fs, f_off, 192, 192, nb.T2, nb.CAT2, nb.Fa, nb.Tt));
+  HIMO_RET(up_block(2, nb.Tt, Bs, b_off, 96, 96, nb.T3, nb.CAT3, nb.X3, nb.U));
   HIMO_RET(conv(nb.U, 0, 96, 1, w->dec4_w, w->dec4_b, 96, 3, 1, 0, nb.U, 0, P, stream, w->dec4_s, nb.V));
 
   mark(2);

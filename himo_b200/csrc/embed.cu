@@ -58,6 +58,7 @@ struct EmbedArgs {
   __nv_bfloat16* canvas;       // [planes][gy][gx][F*32]
   int canvas_planes;
   long long canvas_plane_stride;
+  int canvas_ld;               // channels per pixel of the buffer the canvas lives in (>= F*32)
   const float* pfn_w;   // [32][9] BN-folded
   const float* pfn_b;   // [32]    BN-folded
 };
@@ -264,7 +265,7 @@ k_embed_pfn(EmbedArgs a, EmbedGrid g) {
       a.voxel_mean[((size_t)f * a.n_max + v) * 3 + lane] = lane == 0 ? mx : (lane == 1 ? my : mz);
     if (a.voxel_key && lane == 0) a.voxel_key[(size_t)f * a.n_max + v] = key;
     // canvas[:, y*512+x] = voxel_feats.T  (encoder.py:140-146), NHWC, channel slice of this frame
-    umma::store_split(a.canvas + (size_t)key * C + f * 32 + lane, a.canvas_plane_stride, a.canvas_planes, feat);
+    umma::store_split(a.canvas + (size_t)key * a.canvas_ld + f * 32 + lane, a.canvas_plane_stride, a.canvas_planes, feat);
   }
 }
 
@@ -350,7 +351,7 @@ k_embed_pfn_big(EmbedArgs a, EmbedGrid g) {
       if (a.voxel_mean && lane < 3)
         a.voxel_mean[((size_t)f * a.n_max + v) * 3 + lane] = lane == 0 ? mx : (lane == 1 ? my : mz);
       if (a.voxel_key && lane == 0) a.voxel_key[(size_t)f * a.n_max + v] = key;
-      umma::store_split(a.canvas + (size_t)key * C + f * 32 + lane, a.canvas_plane_stride, a.canvas_planes, feat);
+      umma::store_split(a.canvas + (size_t)key * a.canvas_ld + f * 32 + lane, a.canvas_plane_stride, a.canvas_planes, feat);
     }
     __syncthreads();
   }
@@ -396,6 +397,20 @@ extern "C" size_t himo_embed_workspace_bytes(int n_frames, int n_max, const floa
   return embed_ws_layout(n_frames, n_max, gx * gy / 32 + 1, nullptr, nullptr);
 }
 
+namespace himo {
+// zero the channel slice [0, chunks*16 bytes) of every pixel of an NHWC buffer with `ld16` 16-byte units per pixel
+// (cudaMemset2DAsync does this at a fraction of the HBM rate for 192-byte rows)
+__global__ void __launch_bounds__(256)
+k_clear_slice(uint4* __restrict__ base, int ld16, int chunks, long long total) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / chunks;
+    const int c = (int)(i - pix * chunks);
+    base[pix * ld16 + c] = z;
+  }
+}
+}  // namespace himo
+
 extern "C" int himo_embed_frames(const himo_embed_desc* d, void* stream_) {
   if (!d || d->n_frames <= 0 || d->n_frames > HIMO_MAX_FRAMES || !d->canvas || !d->workspace) return HIMO_ERR_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -429,9 +444,14 @@ extern "C" int himo_embed_frames(const himo_embed_desc* d, void* stream_) {
   a.n_words = a.n_cells / 32 + 1;
   const size_t need = embed_ws_layout(d->n_frames, d->n_max, a.n_words, &a, d->workspace);
   if (need > d->workspace_bytes) return HIMO_ERR_WORKSPACE;
-  a.canvas = (__nv_bfloat16*)d->canvas;
+  // the canvas may be a channel slice [canvas_ch_off, +F*32) of a wider NHWC buffer (the backbone's concatenation
+  // buffer: the skip connection of the last UpsampleSkip block then costs no copy)
+  a.canvas_ld = d->canvas_ld > 0 ? d->canvas_ld : d->n_frames * 32;
+  if (a.canvas_ld < d->n_frames * 32 + d->canvas_ch_off || d->canvas_ch_off < 0 || (a.canvas_ld % 8) || (d->canvas_ch_off % 8))
+    return HIMO_ERR_ARG;
+  a.canvas = (__nv_bfloat16*)d->canvas + d->canvas_ch_off;
   a.canvas_planes = d->canvas_planes;
-  a.canvas_plane_stride = (long long)g.gx * g.gy * d->n_frames * 32;
+  a.canvas_plane_stride = (long long)g.gx * g.gy * a.canvas_ld;
   a.pfn_w = d->pfn_weight; a.pfn_b = d->pfn_bias;
   if (!a.pfn_w || !a.pfn_b || (d->canvas_planes != 1 && d->canvas_planes != 2)) return HIMO_ERR_ARG;
 
@@ -439,8 +459,16 @@ extern "C" int himo_embed_frames(const himo_embed_desc* d, void* stream_) {
   HIMO_CUDA_RET(cudaMemsetAsync(a.bitmap, 0, F * a.n_words * sizeof(unsigned), stream));
   HIMO_CUDA_RET(cudaMemsetAsync(a.count, 0, F * (N + 1) * sizeof(int), stream));
   HIMO_CUDA_RET(cudaMemsetAsync(a.big_count, 0, F * sizeof(int), stream));
-  if (!d->skip_canvas_clear)
-    HIMO_CUDA_RET(cudaMemsetAsync(a.canvas, 0, (size_t)a.canvas_plane_stride * d->canvas_planes * 2, stream));
+  if (!d->skip_canvas_clear) {
+    if (a.canvas_ld == d->n_frames * 32)
+      HIMO_CUDA_RET(cudaMemsetAsync(a.canvas, 0, (size_t)a.canvas_plane_stride * d->canvas_planes * 2, stream));
+    else {  // channel slice of a wider buffer: the planes follow each other at the same pitch, one strided clear
+      const int chunks = d->n_frames * 32 * 2 / 16;
+      const long long total = (long long)g.gx * g.gy * d->canvas_planes * chunks;
+      k_clear_slice<<<kNumSMs * 8, 256, 0, stream>>>((uint4*)a.canvas, a.canvas_ld * 2 / 16, chunks, total);
+      HIMO_LAUNCH_RET();
+    }
+  }
   if (n_max > 0) {
     dim3 gp(min(ceil_div(n_max, 256), kNumSMs * 8), d->n_frames);
     k_embed_points<<<gp, 256, 0, stream>>>(a, g);

@@ -8,6 +8,7 @@ C-ABI call, `himo_deflowpp_forward` (csrc/deflowpp.cu); there is no PyTorch fall
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_float, c_int, c_int32, c_size_t, c_void_p
 from typing import Dict, List, Optional
 
@@ -33,6 +34,7 @@ class _Weights(ctypes.Structure):
         ("dec2_w", c_void_p), ("dec2_b", c_void_p),
         ("enc_s", c_float * 16), ("dec_s", (c_float * 4) * 3), ("dec4_s", c_float),
         ("gru_zr_s", c_float), ("gru_q_s", c_float), ("dec0_s", c_float),
+        ("dec_bb", c_void_p * 3),
     ]
 
 
@@ -61,6 +63,28 @@ _lib.register("himo_rigid_flow", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_
 _lib.register("himo_final_flow", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p])
 _lib.register("himo_launch_count", ctypes.c_ulonglong, [])
 _lib.register("himo_deflowpp_set_fused_decoder", c_int, [c_int])
+
+
+def compose_u3_u4(w3: torch.Tensor, b3: torch.Tensor, w4: torch.Tensor, b4: torch.Tensor):
+    """UpsampleSkip.forward (OSF/src/models/basic/unet.py:31-35): u4(cat([up(u1(a)), u3(b)])) with u3 a 1x1 and u4 a
+    zero-padded 3x3 convolution and nothing in between.  Returns (W4', b4', border) in float32, composed in float64:
+      W4'[:, :L] = W4[:, :L];  W4'[:, L:, ky, kx] = W4[:, L:, ky, kx] @ W3        (L = latent channels)
+      b4' = b4 + sum over the 9 taps of W4[:, L:, tap] @ b3                        (interior pixels)
+      border[yc][xc] = b4 + sum over the taps that stay inside the image of W4[:, L:, tap] @ b3, yc / xc = 0 first
+      row / column, 1 interior, 2 last: a tap that lands in u4's zero padding sees 0, not u3's bias."""
+    L = w3.shape[0]
+    w3m, b3d = w3.double().reshape(L, -1), b3.double()
+    w4d = w4.double()
+    out = w4d.clone()
+    out[:, L:] = torch.einsum("omyx,mi->oiyx", w4d[:, L:], w3m)
+    tap_bias = torch.einsum("omyx,m->oyx", w4d[:, L:], b3d)                 # [Cout, 3, 3]
+    border = torch.empty(3, 3, w4.shape[0], dtype=torch.float64)
+    for yc in range(3):
+        for xc in range(3):
+            ky = [k for k in range(3) if not (yc == 0 and k == 0) and not (yc == 2 and k == 2)]
+            kx = [k for k in range(3) if not (xc == 0 and k == 0) and not (xc == 2 and k == 2)]
+            border[yc, xc] = b4.double() + tap_bias[:, ky][:, :, kx].sum((1, 2))
+    return out.float(), border[1, 1].float().contiguous(), border.float().contiguous()
 
 
 def cal_pose0to1(pose0: torch.Tensor, pose1: torch.Tensor) -> torch.Tensor:
@@ -98,7 +122,7 @@ class DeFlowPP:
 
     def __init__(self, voxel_size=(0.2, 0.2, 6), point_cloud_range=(-51.2, -51.2, -3, 51.2, 51.2, 3),
                  grid_feature_size=(512, 512), decoder_option="gru", num_iters=2, num_frames=3,
-                 precision: str = "fp32", device="cuda", max_points: int = 131072):
+                 precision: str = "fp32", device="cuda", max_points: int = 131072, compose_skip: Optional[bool] = None):
         if list(voxel_size) != [0.2, 0.2, 6] or list(point_cloud_range) != [-51.2, -51.2, -3, 51.2, 51.2, 3] \
                 or list(grid_feature_size)[:2] != [512, 512]:
             raise NotImplementedError("himo_b200.DeFlowPP is built for the SeFlow++ grid (conf/model/deflowpp.yaml)")
@@ -106,6 +130,9 @@ class DeFlowPP:
             raise NotImplementedError("DeFlowPP only supports the gru decoder with num_frames = 3")
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
+        # UpsampleSkip applies u3 (1x1 on the skip) and u4 (3x3 on the concatenation) back to back with no activation in
+        # between (unet.py:31-35): composed on the host into one 3x3 convolution (see load_state_dict)
+        self.compose_skip = (os.environ.get("HIMO_COMPOSE_SKIP", "1") != "0") if compose_skip is None else bool(compose_skip)
         self.num_iters = int(num_iters)
         self.num_frames = 3
         self.planes = 2 if precision == "fp32" else 1
@@ -152,6 +179,12 @@ class DeFlowPP:
             for j, sub in enumerate((".u1_u2.0", ".u3", ".u4_u5.0", ".u4_u5.1")):
                 w.dec_w[bi][j], w.dec_s[bi][j] = self._pack(sd[q + sub + ".weight"])
                 w.dec_b[bi][j] = self._dev(sd[q + sub + ".bias"].float())
+            if self.compose_skip:
+                w4, b4, bb = compose_u3_u4(sd[q + ".u3.weight"], sd[q + ".u3.bias"], sd[q + ".u4_u5.0.weight"],
+                                           sd[q + ".u4_u5.0.bias"])
+                w.dec_w[bi][2], w.dec_s[bi][2] = self._pack(w4)
+                w.dec_b[bi][2] = self._dev(b4)
+                w.dec_bb[bi] = self._dev(bb)
         w.dec4_w, w.dec4_s = self._pack(sd["backbone.decoder_step4.weight"])
         w.dec4_b = self._dev(sd["backbone.decoder_step4.bias"].float())
         w.off_w = self._dev(sd["head.offset_encoder.weight"].float())
@@ -211,7 +244,7 @@ class DeFlowPP:
                 raise RuntimeError(f"{name} must be a contiguous float32 [N,3] tensor")
         dev = pc0.device
         n_max = max(pch1.shape[0], pc0.shape[0], pc1.shape[0], 1)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             ws = self._workspace(n_max)
             io = _IO()
             io.pch1, io.n_h1 = pch1.data_ptr(), pch1.shape[0]
@@ -286,7 +319,7 @@ def rigid_flow(points: torch.Tensor, T: torch.Tensor, add_flow: Optional[torch.T
     pts = points.contiguous()
     T12 = torch.as_tensor(T)[:3, :4].contiguous().float().flatten().to(dev)
     out = torch.empty_like(pts)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         st = _lib.lib().himo_rigid_flow(_lib.ptr(pts), pts.shape[0], _lib.ptr(T12),
                                         _lib.ptr(add_flow.contiguous()) if add_flow is not None else None,
                                         _lib.ptr(out), _lib.stream_ptr(dev))

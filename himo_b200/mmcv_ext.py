@@ -26,16 +26,23 @@ def dynamic_voxelize_forward(points: torch.Tensor, voxel_size: torch.Tensor,
         raise RuntimeError("coors must be int32 [N,3] (NDim=3)")
     if points.dtype != torch.float32:
         raise RuntimeError("points must be float32")
-    pts = points.contiguous()
+    pts = points if points.is_contiguous() else points.contiguous()
     if not coors.is_contiguous():
         raise RuntimeError("coors must be contiguous")
-    vs = voxel_size.detach().to("cpu", torch.float32).contiguous()
-    cr = coors_range.detach().to("cpu", torch.float32).contiguous()
-    with torch.cuda.device(pts.device):
+    vs, cr = _host_f32(voxel_size), _host_f32(coors_range)
+    with _lib.on_device(pts.device):
         st = _lib.lib().himo_dynamic_voxelize_forward(
             _lib.ptr(pts), pts.shape[0], pts.shape[1], _lib.ptr(vs), _lib.ptr(cr),
             _lib.ptr(coors), _lib.stream_ptr(pts.device))
     _lib.check(st, "dynamic_voxelize_forward")
+
+
+def _host_f32(t: torch.Tensor) -> torch.Tensor:
+    """voxel_size / coors_range as contiguous float32 HOST tensors (they are, in the reference's call: voxelize.py:78-85);
+    anything else is converted."""
+    if t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad:
+        return t
+    return t.detach().to("cpu", torch.float32).contiguous()
 
 
 def hard_voxelize_forward(*args, **kwargs):
@@ -71,7 +78,7 @@ def dynamic_point_to_voxel_forward(feats: torch.Tensor, coors: torch.Tensor, red
     ws_bytes = L.himo_dynamic_point_to_voxel_workspace_bytes(n, c, _lib.ptr(dims_t))
     if ws_bytes == 0:
         raise RuntimeError("dynamic_point_to_voxel_forward: voxel grid too large")
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         ws = _lib.workspace.get(ws_bytes, dev)
         voxel_feats = torch.empty((n, c), dtype=torch.float32, device=dev)
         voxel_coors = torch.empty((n, 3), dtype=coors.dtype, device=dev)

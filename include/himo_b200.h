@@ -149,6 +149,9 @@ typedef struct himo_conv_desc {
    * split(r*h) to out2; act 6 = q GEMM -> h = (1-z)h + z*tanh(.) to aux_h and split(h) to out2 */
   float* aux_h; float* aux_z; int aux_ld;
   void* out2; long long out2_plane_stride; int out2_ld;
+  /* composed (1x1 conv -> zero padding -> 3x3 conv) layers: [3][3][Cout] f32 bias per border class (row class, column
+   * class: 0 first, 1 interior, 2 last); replaces `bias` for the pixels on the image border.  NULL = off. */
+  const float* border_bias;
 } himo_conv_desc;
 int himo_conv2d_nhwc(const himo_conv_desc* desc, void* stream);
 /* Split-mode accuracy/speed knob: hi*hi MMAs (K = 16 each) accumulated in tensor memory before the partial
@@ -170,6 +173,12 @@ int himo_conv_set_wide_tiles(int enable);
 /* A/B knob: 0 disables the weights-resident variants (whole weight tensor in shared memory) of the 64-channel
  * encoder layers (default on). */
 int himo_conv_set_weights_resident(int enable);
+/* A/B knob: 0 disables the two-output-rows tiles (k_conv_rows2: a CTA pair computes 2 rows x 256 px x 96 channels so that
+ * activation rows and weight taps are shared; default on) of the 96-channel 3x3 decoder-half layers. */
+int himo_conv_set_rows2(int enable);
+/* A/B knob: 0 launches the backbone kernels (convolutions, upsample) without programmatic dependent launch, i.e. with
+ * full stream serialisation between them (default on: the next kernel's prologue overlaps the previous kernel's tail). */
+int himo_conv_set_pdl(int enable);
 /* A/B knob: 0 launches one CTA per output tile instead of the persistent tile loop (default on). */
 int himo_conv_set_persistent(int enable);
 /* A/B knob: 0 disables the CTA-pair path (tcgen05.mma.cta_group::2 over a cluster of 2; default on). */
@@ -213,6 +222,10 @@ typedef struct himo_embed_desc {
   int skip_canvas_clear;
   void* workspace;
   size_t workspace_bytes;
+  /* optional: the canvas is the channel slice [canvas_ch_off, +n_frames*32) of a wider NHWC buffer with canvas_ld
+   * channels per pixel (0 = a dense canvas of n_frames*32 channels); `canvas` then points at the buffer's channel 0 */
+  int canvas_ld;
+  int canvas_ch_off;
 } himo_embed_desc;
 typedef struct himo_embed_view {     /* device pointers into the embed workspace, rows = frames */
   float* pt4;            /* [F][n_max][4] warped xyz + int32 cell key (y*gx+x, -1 = dropped) */
@@ -255,6 +268,12 @@ typedef struct himo_deflowpp_weights {
   const float* dec2_w; const float* dec2_b;             /* head.decoder.2 [3,48],[3] */
   /* accumulator scales (inverse of the power-of-two weight pre-scale) per GEMM, 0 = 1 */
   float enc_s[16]; float dec_s[3][4]; float dec4_s; float gru_zr_s; float gru_q_s; float dec0_s;
+  /* UpsampleSkip.forward (unet.py:31-35) applies u3 (1x1, on the skip) and u4 (3x3, on the concatenation) with nothing
+   * in between, so the host may compose them: dec_w[b][2] then holds u4 with its skip half multiplied by u3
+   * (W4[:, latent:] @ W3 per tap), dec_b[b][2] the interior bias b4 + sum_taps W4_tap b3, and dec_bb[b] the
+   * [3][3][Cout] border-class biases (taps that fall into the zero padding do not see b3).  The u3 launch and its
+   * output tensor disappear; every skip producer writes straight into the concatenation buffer.  NULL = not composed. */
+  const float* dec_bb[3];
 } himo_deflowpp_weights;
 typedef struct himo_deflowpp_io {
   const float* pch1; int n_h1;              /* t-1 cloud, ground-free, sensor frame */

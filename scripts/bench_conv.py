@@ -16,6 +16,15 @@ LAYERS = [  # name, H, W, Cin, Cout, ksize, stride, groups, act (1 = bias + GELU
     ("b2.u4 384->192 @256", 256, 256, 384, 192, 3, 1, 1, 0, 0),
     ("b3.u4 192->96 @512", 512, 512, 192, 96, 3, 1, 1, 0, 0),
     ("b3.u5 96->96 @512", 512, 512, 96, 96, 3, 1, 1, 0, 0),
+    ("b2.u5 192->192 @256", 256, 256, 192, 192, 3, 1, 1, 0, 0),
+    ("dec4 96->96 @512 fp32 out", 512, 512, 96, 96, 3, 1, 1, 0, 1),
+    ("probe enc2.1 x6 frames", 128, 128, 128, 128, 3, 1, 6, 1, 0),
+    ("probe enc2.1 x12 frames", 128, 128, 128, 128, 3, 1, 12, 1, 0),
+    ("probe enc2.1 x24 frames", 128, 128, 128, 128, 3, 1, 24, 1, 0),
+    ("probe enc1.1 x6 frames", 256, 256, 64, 64, 3, 1, 6, 1, 0),
+    ("probe enc1.1 x12 frames", 256, 256, 64, 64, 3, 1, 12, 1, 0),
+    ("probe enc3.1 x6 frames", 64, 64, 256, 256, 3, 1, 6, 1, 0),
+    ("probe enc3.1 x12 frames", 64, 64, 256, 256, 3, 1, 12, 1, 0),
     ("gru zr 288->384 x100k", 782, 128, 288, 384, 1, 1, 1, 2, 1),
     ("gru q 288->192 x100k", 782, 128, 288, 192, 1, 1, 1, 3, 1),
 ]
@@ -40,6 +49,10 @@ if os.environ.get("WIDE") is not None:
     L.himo_conv_set_wide_tiles(int(os.environ["WIDE"]))
 if os.environ.get("WRES") is not None:
     L.himo_conv_set_weights_resident(int(os.environ["WRES"]))
+if os.environ.get("ROWS2") is not None:
+    L.himo_conv_set_rows2(int(os.environ["ROWS2"]))
+if os.environ.get("PDL") is not None:
+    L.himo_conv_set_pdl(int(os.environ["PDL"]))
 if os.environ.get("FLUSH") is not None:
     L.himo_conv_set_flush_iters(int(os.environ["FLUSH"]))
 for name, H, W, cin, cout, k, s, g, act, f32 in LAYERS:

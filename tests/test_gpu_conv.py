@@ -59,6 +59,41 @@ def test_conv_gelu_fp32_out_and_groups():
     assert _run(128, 128, 32, 64, 3, 2, planes=2, act=1, groups=3) < 2e-6
 
 
+@pytest.mark.parametrize("H,W,cin,cout,act,fp32", [
+    (8, 256, 192, 96, 0, False),     # k_conv_rows2: two output rows per CTA pair (96-channel decoder-half layers)
+    (6, 512, 96, 192, 1, False),     # two pair columns, two N tiles, GELU
+    (4, 256, 96, 96, 0, True),       # decoder_step4: fp32 output
+    (10, 256, 384, 192, 0, False),   # u4 of decoder_step2: 216 hi*hi MMAs per (uncut) chain
+])
+def test_conv_two_row_tiles(H, W, cin, cout, act, fp32):
+    # the two-row kernel does not cut the hi*hi accumulation chain (54-216 tensor-core accumulations, each truncating):
+    # measured 3.3e-6 of the output scale at 108 MMAs, against < 2e-6 for the 48-MMA chains of k_conv_umma
+    assert _run(H, W, cin, cout, 3, 1, planes=2, act=act, out_fp32=fp32) < 6e-6
+
+
+@pytest.mark.parametrize("H,W,L,cout", [(6, 256, 96, 96), (8, 128, 64, 128)])
+def test_composed_u3_u4_with_border_bias(H, W, L, cout):
+    """UpsampleSkip (unet.py:31-35): u4(cat([a, u3(b)])) as ONE 3x3 convolution with composed weights and the
+    border-class biases (himo_b200.deflowpp.compose_u3_u4) against the two torch convolutions."""
+    from himo_b200.deflowpp import compose_u3_u4
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.randn(1, L, H, W, generator=g), torch.randn(1, L, H, W, generator=g)
+    w3 = torch.randn(L, L, 1, 1, generator=g) / np.sqrt(L)
+    b3 = torch.randn(L, generator=g)
+    w4 = torch.randn(cout, 2 * L, 3, 3, generator=g) / np.sqrt(18 * L)
+    b4 = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(torch.cat([a, F.conv2d(b, w3, b3)], 1), w4, b4, padding=1)[0].permute(1, 2, 0)
+    wc, bc, bb = compose_u3_u4(w3, b3, w4, b4)
+    x = torch.cat([a, b], 1)[0].permute(1, 2, 0).contiguous()
+    xp = conv.split_planes(x.cuda(), 2)
+    ws = conv.weight_prescale(wc, 2)
+    wp = conv.pack_conv_weight(wc, 2, ws).cuda()
+    out = torch.zeros((2, H, W, cout), dtype=torch.bfloat16, device="cuda")
+    conv.conv2d_nhwc(xp, wp, bc.cuda(), out, ksize=3, acc_scale=1.0 / ws, border_bias=bb.cuda())
+    got = conv.merge_planes(out).cpu()
+    assert (got - ref).abs().max().item() / ref.abs().max().item() < 3e-6
+
+
 def test_conv_single_plane_bf16():
     assert _run(128, 128, 64, 64, 3, 1, planes=1) < 2e-2
     assert _run(128, 128, 192, 96, 3, 1, planes=1, act=1) < 2e-2
