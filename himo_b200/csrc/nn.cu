@@ -505,6 +505,208 @@ k_nn_search(NNCloud c0, NNCloud c1, const NNGrid* __restrict__ gp, float* __rest
   }
 }
 
+// ---- warp-cooperative search ---------------------------------------------------------------------------------
+// One WARP per query (queries in Morton order, so neighbouring warps walk the same nodes and share them in L1/L2).
+// Control flow is uniform across the warp; the lanes share the work of a query instead of each owning one:
+//   * start level: lane l looks up the population of the level-l node around the query (two rank lookups per lane,
+//     all levels at once); the search starts at the finest level whose node holds >= kNNWStart points, so that a leaf
+//     scan fills the warp (0.5 m lidar cells hold ~4 points: scanning them one by one leaves 28 lanes idle);
+//   * 3x3x3 probe: lane t < 27 owns neighbour node t -- box distance, key, point range -- and the warp then visits the
+//     surviving nodes nearest first (redux.sync min over the box distances + ballot), re-pruning after every scan;
+//   * leaf scan: lanes read CONSECUTIVE float4 of the sorted reference cloud (one 512-byte coalesced request per step),
+//     each lane keeps its own (best, index); the warp-wide bound is one redux.sync min over the distance bits;
+//   * crowded nodes (> kNNWLeaf points) are descended depth-first with a per-warp stack in shared memory; the <= 8
+//     children are evaluated by 8 lanes and pushed farthest first;
+//   * the result is the 64-bit min over the lanes of (distance bits << 32 | index): ties resolve to the lowest index,
+//     the reference's rule (chamfer3D.cu:61-69 scans j ascending with a strict <).
+// Exactness is the per-thread kernel's: the same box bounds (projection onto the grid box, eps slack) and the same slab
+// bound end the level loop; only the order in which candidates are tested differs, and (best, index) is order-free.
+constexpr int kNNWLeaf = 256;    // nodes up to this many points are scanned (8 coalesced steps), larger ones descended
+constexpr int kNNWStart = 24;    // start at the finest level whose centre node holds at least this many points
+constexpr int kNNWWarps = 4;
+
+__device__ __forceinline__ void nnw_scan(const float4* __restrict__ rs, int s, int e, int lane, const NNQuery& qq,
+                                         float& best, int& best_i) {
+  for (int j = s + lane; j < e; j += 32) {
+    const float4 c = __ldg(rs + j);
+    const float dx = c.x - qq.x, dy = c.y - qq.y, dz = c.z - qq.z;
+    const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    const int ci = __float_as_int(c.w);
+    if (d < best || (d == best && ci < best_i)) { best = d; best_i = ci; }
+  }
+}
+
+__global__ void __launch_bounds__(32 * kNNWWarps)
+k_nn_search_warp(NNCloud c0, NNCloud c1, const NNGrid* __restrict__ gp, float* __restrict__ dist0,
+                 int32_t* __restrict__ idx0, float* __restrict__ dist1, int32_t* __restrict__ idx1, float radius2) {
+  __shared__ unsigned s_stack[kNNWWarps][96];
+  const NNGrid g = *gp;
+  const NNCloud& qc = blockIdx.y == 0 ? c0 : c1;
+  const NNCloud& rc = blockIdx.y == 0 ? c1 : c0;
+  float* __restrict__ dist = blockIdx.y == 0 ? dist0 : dist1;
+  int32_t* __restrict__ idx = blockIdx.y == 0 ? idx0 : idx1;
+  NNRef r;
+  r.bitmap = rc.bitmap; r.prefix = rc.word_prefix; r.cstart = rc.cell_start; r.rs = rc.sorted;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned* stack = s_stack[wib];
+  const unsigned FULL = 0xffffffffu;
+  const int nxy = 1 << g.bxy, nz = 1 << g.bz;
+  const int top = g.bxy;
+  const float ex = g.h * (float)nxy, ez = g.h * (float)nz;
+  for (int t = blockIdx.x * kNNWWarps + wib; t < qc.n; t += gridDim.x * kNNWWarps) {
+    const float4 p = qc.sorted[t];                       // same address in every lane: one broadcast load
+    const int qi = __float_as_int(p.w);
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) {   // the reference's comparisons all fail on NaN
+      if (lane == 0) { dist[qi] = 1e20f; idx[qi] = -1; }
+      continue;
+    }
+    NNQuery q;
+    q.x = p.x; q.y = p.y; q.z = p.z;
+    q.px = fminf(fmaxf(p.x, g.ox), g.ox + ex);
+    q.py = fminf(fmaxf(p.y, g.oy), g.oy + ex);
+    q.pz = fminf(fmaxf(p.z, g.oz), g.oz + ez);
+    float best = radius2;            // lane-private running minimum
+    int best_i = -1;
+    float best_w = radius2;          // warp-wide bound used for pruning (uniform)
+    int cx, cy, cz;
+    nn_cell(g, p.x, p.y, p.z, cx, cy, cz);
+    const unsigned kq = nn_key(g, cx, cy, cz);
+    // ---- start level: lane l counts the level-l node around the query
+    int lvl0;
+    {
+      int cnt = 0;
+      if (lane <= top) {
+        const unsigned size = 1u << nn_level_bits(g, lane);
+        int s, e;
+        nn_node_range(g, r, kq & ~(size - 1u), lane, s, e);
+        cnt = e - s;
+      }
+      const unsigned m = __ballot_sync(FULL, lane <= top && cnt >= kNNWStart);
+      lvl0 = m ? __ffs(m) - 1 : top;
+    }
+    for (int lvl = lvl0; lvl <= top; ++lvl) {
+      const float H = g.h * (float)(1 << lvl);
+      const int kx = cx >> lvl, ky = cy >> lvl, kz = lvl < g.bz ? cz >> lvl : 0;
+      const int mxy = max(nxy >> lvl, 1), mz = max(nz >> lvl, 1);
+      // ---- probe: lane t27 owns one of the 3x3x3 nodes
+      int ns = 0, ne = 0;
+      unsigned nbase = 0u, nkey = 0xffffffffu;      // nkey: box-distance bits while the node is still to be visited
+      if (lane < 27 && !(lvl != lvl0 && lane == 13)) {   // later levels: the centre is the parent of the slab already examined
+        const int iz = lane / 9, iy = (lane - 9 * iz) / 3, ix = lane - 9 * iz - 3 * iy;
+        const int x = kx + ix - 1, y = ky + iy - 1, z = kz + iz - 1;
+        if (x >= 0 && x < mxy && y >= 0 && y < mxy && z >= 0 && z < mz) {
+          const float d2 = nn_box_d2(g, q, lvl, x, y, z);
+          if (d2 <= best_w) {
+            nbase = nn_key(g, x << lvl, y << lvl, z << lvl);
+            nn_node_range(g, r, nbase, lvl, ns, ne);
+            if (ne > ns) nkey = __float_as_uint(d2);
+          }
+        }
+      }
+      // ---- visit the surviving nodes nearest first
+      while (true) {
+        if (nkey != 0xffffffffu && __uint_as_float(nkey) > best_w) nkey = 0xffffffffu;
+        const unsigned mn = __reduce_min_sync(FULL, nkey);
+        if (mn == 0xffffffffu) break;
+        const int src = __ffs(__ballot_sync(FULL, nkey == mn)) - 1;
+        const int s = __shfl_sync(FULL, ns, src), e = __shfl_sync(FULL, ne, src);
+        const unsigned base = __shfl_sync(FULL, nbase, src);
+        if (lane == src) nkey = 0xffffffffu;
+        if (e - s <= kNNWLeaf || lvl == 0) {
+          nnw_scan(r.rs, s, e, lane, q, best, best_i);
+        } else {
+          // ---- depth-first descent, nearest child first (uniform control flow; 8 lanes evaluate the children)
+          int sp = 0;
+          if (lane == 0) stack[0] = base | ((unsigned)lvl << 28);
+          sp = 1;
+          __syncwarp();
+          while (sp > 0) {
+            const unsigned ent = stack[--sp];
+            __syncwarp();
+            const unsigned nb = ent & ((1u << 28) - 1u);
+            const int nl = (int)(ent >> 28);
+            int bx_, by_, bz_;
+            nn_unkey(g, nb, bx_, by_, bz_);
+            if (nn_box_d2(g, q, nl, bx_ >> nl, by_ >> nl, bz_ >> nl) > best_w) continue;
+            int cs, ce;
+            nn_node_range(g, r, nb, nl, cs, ce);
+            if (cs == ce) continue;
+            if (ce - cs <= kNNWLeaf || nl == 0) {
+              nnw_scan(r.rs, cs, ce, lane, q, best, best_i);
+              best_w = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(best)));
+              continue;
+            }
+            const int cl = nl - 1;
+            const bool sxy = cl < g.bxy, sz = cl < g.bz;
+            const unsigned xb = nn_xbit(g, cl), zb = 4u << (3 * cl);
+            const float Hc = g.h * (float)(1 << cl);
+            const float lx = g.ox + (float)bx_ * g.h, ly = g.oy + (float)by_ * g.h, lz = g.oz + (float)bz_ * g.h;
+            const int nchild = (sxy ? 4 : 1) * (sz ? 2 : 1);
+            unsigned ckey = 0u, ckd = 0xffffffffu;
+            if (lane < nchild) {
+              int ix = 0, iy = 0, iz = 0, mm = lane;
+              if (sxy) { ix = mm & 1; iy = (mm >> 1) & 1; mm >>= 2; }
+              if (sz) iz = mm & 1;
+              const float ox_ = lx + (float)ix * Hc, oy_ = ly + (float)iy * Hc, oz_ = lz + (float)iz * Hc;
+              const float wxy = sxy ? Hc : 2.f * Hc, wz = sz ? Hc : 2.f * Hc;      // an axis that does not split keeps the parent's extent
+              const float tx = fmaxf(fmaxf(ox_ - q.px, q.px - (ox_ + wxy)) - g.eps, 0.f);
+              const float ty = fmaxf(fmaxf(oy_ - q.py, q.py - (oy_ + wxy)) - g.eps, 0.f);
+              const float tz = fmaxf(fmaxf(oz_ - q.pz, q.pz - (oz_ + wz)) - g.eps, 0.f);
+              const float cd = tx * tx + ty * ty + tz * tz;
+              if (cd <= best_w) {
+                ckey = nb | (ix ? xb : 0u) | (iy ? xb << 1 : 0u) | (iz ? zb : 0u);
+                int s2, e2;
+                nn_node_range(g, r, ckey, cl, s2, e2);
+                if (e2 > s2) ckd = __float_as_uint(cd);
+              }
+            }
+            // rank of this child among the valid ones by (distance, lane): nearest = rank 0
+            const unsigned vmask = __ballot_sync(FULL, ckd != 0xffffffffu);
+            const int nvalid = __popc(vmask);
+            int rank = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const unsigned kj = __shfl_sync(FULL, ckd, j);
+              rank += (kj < ckd || (kj == ckd && j < lane)) ? 1 : 0;
+            }
+            if (ckd != 0xffffffffu && sp + nvalid <= 96) stack[sp + (nvalid - 1 - rank)] = ckey | ((unsigned)cl << 28);
+            if (sp + nvalid <= 96) sp += nvalid;
+            else {   // cannot happen (depth <= 13, <= 7 pending siblings per level); scan rather than drop
+              nnw_scan(r.rs, cs, ce, lane, q, best, best_i);
+              best_w = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(best)));
+            }
+            __syncwarp();
+          }
+        }
+        best_w = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(best)));
+      }
+      // everything stored outside the 3x3x3 slab is at least `bound` away (sides cut by the grid edge are open)
+      float bound = INFINITY;
+      if (kx - 1 >= 0) bound = fminf(bound, q.px - (g.ox + (float)(kx - 1) * H));
+      if (kx + 1 < mxy) bound = fminf(bound, (g.ox + (float)(kx + 2) * H) - q.px);
+      if (ky - 1 >= 0) bound = fminf(bound, q.py - (g.oy + (float)(ky - 1) * H));
+      if (ky + 1 < mxy) bound = fminf(bound, (g.oy + (float)(ky + 2) * H) - q.py);
+      if (kz - 1 >= 0) bound = fminf(bound, q.pz - (g.oz + (float)(kz - 1) * H));
+      if (kz + 1 < mz) bound = fminf(bound, (g.oz + (float)(kz + 2) * H) - q.pz);
+      bound -= g.eps;
+      if (bound == INFINITY) break;
+      if (bound > 0.f && best_w < bound * bound) break;
+    }
+    // ---- 64-bit min over the lanes: (distance bits, index); an untouched lane holds (radius2, -1) and sorts last
+    unsigned long long pk = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)best_i;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(FULL, pk, d);
+      pk = o < pk ? o : pk;
+    }
+    if (lane == 0) {
+      const int bi = (int)(unsigned)(pk & 0xffffffffull);
+      dist[qi] = bi < 0 ? 1e20f : __uint_as_float((unsigned)(pk >> 32));
+      idx[qi] = bi;
+    }
+  }
+}
+
 __global__ void k_nn_fill_empty(float* dist, int32_t* idx, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     dist[i] = 1e20f;
@@ -553,6 +755,15 @@ extern "C" size_t himo_chamfer_workspace_bytes(int n0, int n1) {
   const long long mw = nn_max_words((long long)n0 + n1);
   return nn_cloud_bytes(n0, mw) + nn_cloud_bytes(n1, mw) + 4096 + 16 * 256;
 }
+
+// The warp-per-query kernel returns identical results but is SLOWER on every measured cloud (B200, round 2,
+// profiles/r02_nn_warp_vs_thread.jsonl: lidar 100 k 0.78 vs 0.65 ms, uniform 100 k 0.31 vs 0.18 ms, lidar 1 M 13.7 vs
+// 3.85 ms): the search is bound by chains of dependent loads (bitmap word -> prefix -> cell start -> points), and a
+// warp that owns one query has one such chain in flight where a warp of 32 single-thread queries has 32.  Coalesced
+// scans and shuffle reductions do not pay for a 32x loss of memory-level parallelism.  Kept as an A/B knob.
+static int g_nn_warp = 0;
+// A/B knob: 1 selects the warp-cooperative search kernel (one warp per query) instead of one thread per query.
+extern "C" int himo_chamfer_set_warp_search(int enable) { g_nn_warp = enable ? 1 : 0; return HIMO_OK; }
 
 static int nn_forward_impl(const float* pc0, int n0, const float* pc1, int n1, float* dist0,
                            float* dist1, int32_t* idx0, int32_t* idx1, float cell_size, float radius2,
@@ -616,8 +827,13 @@ static int nn_forward_impl(const float* pc0, int n0, const float* pc1, int n1, f
                                  scan_c[k], stream));
   k_nn_fill<<<grid2, 256, 0, stream>>>(c[0], c[1]);
   HIMO_LAUNCH_RET();
-  dim3 grid3(ceil_div(nmax, 128), 2);
-  k_nn_search<<<grid3, 128, 0, stream>>>(c[0], c[1], grid, dist0, idx0, dist1, idx1, radius2);
+  if (g_nn_warp) {   // one warp per query, 32 resident warps per SM
+    dim3 grid3(min(ceil_div(nmax, kNNWWarps), kNumSMs * 16), 2);
+    k_nn_search_warp<<<grid3, 32 * kNNWWarps, 0, stream>>>(c[0], c[1], grid, dist0, idx0, dist1, idx1, radius2);
+  } else {
+    dim3 grid3(ceil_div(nmax, 128), 2);
+    k_nn_search<<<grid3, 128, 0, stream>>>(c[0], c[1], grid, dist0, idx0, dist1, idx1, radius2);
+  }
   HIMO_LAUNCH_RET();
   return HIMO_OK;
 }

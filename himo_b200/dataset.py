@@ -9,6 +9,8 @@ frame-assembly rules, same keys in the returned dict as OSF/src/dataset.py:186-3
 from __future__ import annotations
 
 import os
+import threading
+from collections import OrderedDict
 from typing import Dict, List
 
 import numpy as np
@@ -43,6 +45,25 @@ class HDF5Dataset:
             if ts > b["max_timestamp"]:
                 b["max_timestamp"], b["max_index"] = ts, idx
         self._pos = {(s, str(t)): i for i, (s, t) in enumerate(self.data_index)}
+        # consecutive items share clouds (frame t is pc1 of item t-1, pc0 of item t and pch1 of item t+1): a small LRU
+        # over (scene, timestamp, name) turns three reads per item into one
+        self._cache: "OrderedDict" = OrderedDict()
+        self._cache_cap = 48
+        self._cache_lock = threading.Lock()
+
+    def _read(self, scene_id, ts, name):
+        key = (scene_id, str(ts), name)
+        with self._cache_lock:
+            hit = self._cache.get(key)
+            if hit is not None:
+                self._cache.move_to_end(key)
+                return hit
+        arr = self.store.read(scene_id, ts, name)
+        with self._cache_lock:
+            self._cache[key] = arr
+            while len(self._cache) > self._cache_cap:
+                self._cache.popitem(last=False)
+        return arr
 
     def __len__(self):
         return len(self.eval_data_index) if self.eval_index else len(self.data_index)
@@ -65,19 +86,20 @@ class HDF5Dataset:
         scene_id, ts = self.data_index[index_]
         st = self.store
         d = {"scene_id": scene_id, "timestamp": ts, "eval_flag": eval_flag}
-        d["pc0"] = st.read(scene_id, ts, "lidar")[:, :3]
-        d["gm0"] = st.read(scene_id, ts, "ground_mask")
-        d["pose0"] = st.read(scene_id, ts, "pose")
+        rd = self._read
+        d["pc0"] = rd(scene_id, ts, "lidar")[:, :3]
+        d["gm0"] = rd(scene_id, ts, "ground_mask")
+        d["pose0"] = rd(scene_id, ts, "pose")
         nts = self.data_index[index_ + 1][1]
-        d["pose1"] = st.read(scene_id, nts, "pose")
-        d["pc1"] = st.read(scene_id, nts, "lidar")[:, :3]
-        d["gm1"] = st.read(scene_id, nts, "ground_mask")
+        d["pose1"] = rd(scene_id, nts, "pose")
+        d["pc1"] = rd(scene_id, nts, "lidar")[:, :3]
+        d["gm1"] = rd(scene_id, nts, "ground_mask")
         for i in range(1, self.history_frames + 1):
             fi = max(index_ - i, self.scene_id_bounds[scene_id]["min_index"])
             pts = self.data_index[fi][1]
-            d[f"pch{i}"] = st.read(scene_id, pts, "lidar")[:, :3]
-            d[f"gmh{i}"] = st.read(scene_id, pts, "ground_mask")
-            d[f"poseh{i}"] = st.read(scene_id, pts, "pose")
+            d[f"pch{i}"] = rd(scene_id, pts, "lidar")[:, :3]
+            d[f"gmh{i}"] = rd(scene_id, pts, "ground_mask")
+            d[f"poseh{i}"] = rd(scene_id, pts, "pose")
         for key in [v for v in self.vis_name if v] + _EXTRA:
             if st.has(scene_id, ts, key):
                 d[key] = st.read(scene_id, ts, key)

@@ -52,30 +52,31 @@ def parse_overrides(argv: List[str], aliases: Optional[Dict[str, str]] = None) -
 
 
 class _Prefetch:
-    """Reader thread: `fetch(i)` for i in `indices`, up to `depth` frames ahead of the consumer (the reference gets the
-    same overlap from DataLoader workers, OSF/src/runner.py:123-127)."""
+    """Reader pool: `fetch(i)` for i in `indices` on `workers` threads, results handed over IN ORDER, at most `depth`
+    frames ahead of the consumer (the reference gets the same overlap from DataLoader workers, OSF/src/runner.py:123-127;
+    np.load / h5 reads release the GIL, so threads are enough)."""
 
-    def __init__(self, fetch: Callable[[int], Dict], indices: Iterable[int], depth: int = 4):
-        self.q: "queue.Queue" = queue.Queue(maxsize=depth)
-        self.t = threading.Thread(target=self._run, args=(fetch, list(indices)), daemon=True)
-        self.t.start()
-
-    def _run(self, fetch, indices):
-        try:
-            for i in indices:
-                self.q.put((i, fetch(i)))
-            self.q.put(None)
-        except BaseException as e:              # surfaced in the consumer, never swallowed
-            self.q.put(e)
+    def __init__(self, fetch: Callable[[int], Dict], indices: Iterable[int], depth: int = 8, workers: int = 4):
+        from concurrent.futures import ThreadPoolExecutor
+        self.fetch, self.indices, self.depth = fetch, list(indices), max(1, depth)
+        self.pool = ThreadPoolExecutor(max_workers=max(1, workers), thread_name_prefix="himo-read")
 
     def __iter__(self) -> Iterator[Tuple[int, Dict]]:
-        while True:
-            it = self.q.get()
-            if it is None:
-                return
-            if isinstance(it, BaseException):
-                raise it
-            yield it
+        pending: deque = deque()
+        it = iter(self.indices)
+        try:
+            for i in it:
+                pending.append((i, self.pool.submit(self.fetch, i)))
+                if len(pending) >= self.depth:
+                    j, fut = pending.popleft()
+                    yield j, fut.result()          # a reader exception surfaces here, in the consumer
+            while pending:
+                j, fut = pending.popleft()
+                yield j, fut.result()
+        finally:
+            for _, fut in pending:
+                fut.cancel()
+            self.pool.shutdown(wait=False)
 
 
 class _Writer:
@@ -187,15 +188,17 @@ def shard_frames(n_frames: int, rank: int, world: int) -> range:
     return range(rank * n_frames // world, (rank + 1) * n_frames // world)
 
 
-def run_save(cfg: Dict[str, str], engine=None, n_frames: Optional[int] = None) -> int:
+def run_save(cfg: Dict[str, str], engine=None, n_frames: Optional[int] = None,
+             dist_env: Optional[Tuple[int, int, int]] = None) -> int:
     """`python save.py checkpoint=... dataset_path=... [res_name=...] [shard=frame|scene]` / `python save.py model=fastnsf
     dataset_path=...` (README.md:47-54; OSF/save.py:25-58, OSF/src/runner.py:316-343).  The reference shards by scene
     only to keep two processes out of one .h5 file (runner.py:74-80); the per-frame store has no such constraint, so
     frames are dealt in balanced contiguous blocks unless the store is .h5-backed or `shard=scene` is given.
-    `engine` is injectable for the host tests.  Returns the number of frames this rank wrote."""
+    `engine` is injectable for the host tests; `dist_env` = (rank, world, local_rank) overrides the environment (bench.py
+    gives every rank a private store).  Returns the number of frames this rank wrote."""
     from .dataset import HDF5Dataset
     from .store import H5Store
-    rank, world, local = _dist_env()
+    rank, world, local = dist_env if dist_env is not None else _dist_env()
     data_dir = cfg.get("dataset_path") or cfg.get("data_dir")
     if not data_dir:
         raise SystemExit("dataset_path=<dir with index_total.pkl and scene files> is required")

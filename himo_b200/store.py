@@ -198,3 +198,27 @@ def write_synthetic_dataset(directory: str, n_scenes: int = 2, n_frames: int = 6
     write_index(directory, index, "index_total.pkl")
     write_index(directory, eval_index, "index_eval.pkl")
     return st
+
+
+def write_replicated_dataset(directory: str, triples: Sequence[Dict], n_scenes: int, n_frames: int, seed: int = 0,
+                             eval_every: int = 10, store: Optional[FrameStore] = None) -> FrameStore:
+    """A dataset of `n_scenes` x `n_frames` sweeps in the reference's schema built by cycling through the sweeps of a few
+    already generated `frames.lidar_triple` results (their "frames" entry: the three full sweep dicts).  Generating a
+    lidar-shaped 100 k-point sweep costs seconds of host ray casting, so throughput benchmarks of the drivers (bench.py
+    `pipeline`) replicate a handful of sweeps instead; every array is still written and read per frame."""
+    os.makedirs(directory, exist_ok=True)
+    st = store or NpyStore(directory)
+    sweeps = [fr for tr in triples for fr in tr["frames"]]
+    index, eval_index = [], []
+    for s in range(n_scenes):
+        scene = f"scene{seed:02d}_{s:03d}"
+        for k in range(n_frames):
+            ts = str(int(1_000_000_000 + (seed * 100 + s) * 10_000_000 + k * 100_000))
+            for name, arr in sweeps[(s * 3 + k) % len(sweeps)].items():
+                st.write(scene, ts, name, arr)
+            index.append([scene, ts])
+            if 0 < k < n_frames - 1 and k % eval_every == 0:
+                eval_index.append([scene, ts])
+    write_index(directory, index, "index_total.pkl")
+    write_index(directory, eval_index, "index_eval.pkl")
+    return st

@@ -100,6 +100,11 @@ int himo_chamfer_backward(const float* pc0, int n0, const float* pc1, int n1, co
                           const int32_t* idx1, const float* grad_dist0, const float* grad_dist1,
                           float* grad_pc0, float* grad_pc1, void* stream);
 
+/* A/B knob: 1 selects the warp-cooperative search kernel (one warp per query: coalesced leaf scans, redux.sync / shuffle
+ * min-reductions) instead of one thread per query (default 0: identical results, but measured 1.2-3.6x slower on a B200
+ * because the search is latency-bound and a warp per query has 32x fewer dependent-load chains in flight). */
+int himo_chamfer_set_warp_search(int enable);
+
 /* ------------------------------------------------------------------------------------------
  * H4  dense convolution of the SeFlow++ backbone (tcgen05 implicit GEMM) and 2x bilinear upsample
  * replaces: the ATen/cuDNN work behind nn.Conv2d (+ BatchNorm2d + GELU) in
