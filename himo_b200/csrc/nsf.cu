@@ -487,6 +487,164 @@ k_nsf_rowsum_final(NsfBufs b, const float* __restrict__ part, float* __restrict_
   if (out_w0) { out_w0[f * 3] = t[1]; out_w0[f * 3 + 1] = t[2]; out_w0[f * 3 + 2] = t[3]; }
 }
 
+// ------------------------------------------------------------------------------ generic MLP entry points (NSFP)
+// The same 3 -> 128 x 8 -> 3 prior with the loss OUTSIDE: himo_mlp_forward returns the network output, the caller
+// (NSFP: truncated Chamfer of two networks, OSF/src/models/nsfp.py:48-72) computes any loss and hands d loss / d output
+// to himo_mlp_backward, which produces the parameter gradients (kept in the workspace for himo_mlp_adam_step) and,
+// if asked, d loss / d input (NSFP differentiates through the input of its inverse network).
+__global__ void __launch_bounds__(kHeadThreads)
+k_mlp_head_fwd(NsfBufs b, float* __restrict__ out) {
+  if (b.ctl->stop) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n) return;
+  const float* W8 = b.params + nsf_off_w(8);
+  const float* b8 = b.params + nsf_off_b(8);
+  const __nv_bfloat16* hT = b.HT[8];
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+  for (int j = 0; j < 128; ++j) {
+    const float h = load_split(hT + (long long)j * b.n_pad + i, b.ps, b.planes);
+    f0 = fmaf(__ldg(W8 + j), h, f0);
+    f1 = fmaf(__ldg(W8 + 128 + j), h, f1);
+    f2 = fmaf(__ldg(W8 + 256 + j), h, f2);
+  }
+  f0 += __ldg(b8); f1 += __ldg(b8 + 1); f2 += __ldg(b8 + 2);
+  *(float4*)(b.flow + 4 * (size_t)i) = make_float4(f0, f1, f2, 0.f);
+  out[3 * (size_t)i] = f0; out[3 * (size_t)i + 1] = f1; out[3 * (size_t)i + 2] = f2;
+}
+
+// backward entry: d_out [n,3] (true scale) -> delta_8 = (d_out W8) * relu'(h8) as row-major and transposed planes,
+// per-block partials of dW8 / db8 in the layout k_nsf_adam reads (same reductions as k_nsf_head: deterministic)
+__global__ void __launch_bounds__(kHeadThreads)
+k_mlp_head_bwd(NsfBufs b, const float* __restrict__ d_out) {
+  if (b.ctl->stop) return;
+  __shared__ float red[kHeadThreads / 32][4];
+  __shared__ float red_w[kHeadThreads / 32][3][128];
+  const float* W8 = b.params + nsf_off_w(8);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < b.n;
+  const float S = b.grad_scale;
+  const float d0 = live ? d_out[3 * (size_t)i] * S : 0.f, d1 = live ? d_out[3 * (size_t)i + 1] * S : 0.f,
+              d2 = live ? d_out[3 * (size_t)i + 2] * S : 0.f;
+  const __nv_bfloat16* hT = b.HT[8];
+  float* part = b.head_part + (size_t)blockIdx.x * kHeadPart;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool in_pad = i < b.n_pad;
+  const bool split = b.planes == 2;
+  for (int j0 = 0; j0 < 128; j0 += 8) {
+    uint32_t hi[4], lo[4];
+    float dhv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u;
+      const float h = in_pad ? load_split(hT + (long long)j * b.n_pad + i, b.ps, b.planes) : 0.f;
+      float dh = fmaf(d2, __ldg(W8 + 256 + j), fmaf(d1, __ldg(W8 + 128 + j), d0 * __ldg(W8 + j)));
+      if (!(h > 0.f)) dh = 0.f;
+      dhv[u] = dh;
+      if (in_pad) umma::store_split(b.DLT[0] + (long long)j * b.n_pad + i, b.ps, b.planes, dh);
+      float a0 = d0 * h, a1 = d1 * h, a2 = d2 * h;
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, sft);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, sft);
+      }
+      if (lane == 0) { red_w[warp][0][j] = a0; red_w[warp][1][j] = a1; red_w[warp][2][j] = a2; }
+    }
+    if (in_pad) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) umma::pack_split2(dhv[2 * u], dhv[2 * u + 1], split, hi[u], lo[u]);
+      *(uint4*)(b.DL[0] + (long long)i * 128 + j0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (split) *(uint4*)(b.DL[0] + b.ps + (long long)i * 128 + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 384; t += kHeadThreads) {
+    const int k = t >> 7, j = t & 127;
+    float sacc = 0.f;
+    for (int wv = 0; wv < kHeadThreads / 32; ++wv) sacc += red_w[wv][k][j];
+    part[k * 128 + j] = sacc;
+  }
+  float a0 = d0, a1 = d1, a2 = d2;
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, sft);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, sft);
+  }
+  if (lane == 0) { red[warp][0] = a0; red[warp][1] = a1; red[warp][2] = a2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int wv = 0; wv < kHeadThreads / 32; ++wv) t += red[wv][threadIdx.x];
+    part[384 + threadIdx.x] = t;
+  }
+  if (threadIdx.x == 3) part[387] = 0.f;
+}
+
+// d loss / d input = delta_1 W0 (the only path from the input: h1 = relu(W0 x + b0)); delta_1 row-major planes
+__global__ void __launch_bounds__(128)
+k_mlp_dx(NsfBufs b, const __nv_bfloat16* __restrict__ delta1, float inv_scale, float* __restrict__ dx) {
+  if (b.ctl->stop) return;
+  __shared__ float sW[384];
+  for (int t = threadIdx.x; t < 384; t += 128) sW[t] = b.params[nsf_off_w(0) + t];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n) return;
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  for (int j0 = 0; j0 < 128; j0 += 8) {
+    const uint4 a = *(const uint4*)(delta1 + (long long)i * 128 + j0);
+    const uint32_t aa[4] = {a.x, a.y, a.z, a.w};
+    float v[8];
+    if (b.planes == 2) {
+      const uint4 l = *(const uint4*)(delta1 + b.ps + (long long)i * 128 + j0);
+      const uint32_t ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&aa[k]));
+        const float2 l2 = __half22float2(*reinterpret_cast<const __half2*>(&ll[k]));
+        v[2 * k] = h2.x + l2.x; v[2 * k + 1] = h2.y + l2.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { v[2 * k] = __uint_as_float(aa[k] << 16); v[2 * k + 1] = __uint_as_float(aa[k] & 0xffff0000u); }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = j0 + k;
+      g0 = fmaf(v[k], sW[j * 3], g0); g1 = fmaf(v[k], sW[j * 3 + 1], g1); g2 = fmaf(v[k], sW[j * 3 + 2], g2);
+    }
+  }
+  dx[3 * (size_t)i] = g0 * inv_scale; dx[3 * (size_t)i + 1] = g1 * inv_scale; dx[3 * (size_t)i + 2] = g2 * inv_scale;
+}
+
+// best-so-far bookkeeping + EarlyStopping.step on a loss the CALLER computed (device scalar), same state machine as
+// k_nsf_control (nsfp.py:104-113, nsfp_module.py:60-82).  Counts the iteration: Adam's bias correction reads ctl->iters.
+__global__ void k_mlp_control(NsfCtl* c, const float* __restrict__ loss_dev, float min_delta, int patience) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (c->stop) { c->snapshot = 0; return; }
+  const float loss = *loss_dev;
+  c->loss = loss;
+  c->iters += 1;
+  c->snapshot = 0;
+  if (loss <= c->best_loss) { c->best_loss = loss; c->snapshot = 1; }
+  int stop = 0;
+  if (patience == 0) stop = 0;
+  else if (!c->es_has_best) { c->es_has_best = 1; c->es_best = loss; }
+  else if (isnan(loss)) stop = 1;
+  else {
+    if (loss < c->es_best - min_delta) { c->es_bad = 0; c->es_best = loss; }
+    else c->es_bad += 1;
+    if (c->es_bad >= patience) stop = 1;
+  }
+  c->stop = stop;
+}
+__global__ void __launch_bounds__(256)
+k_mlp_snapshot(const NsfCtl* __restrict__ c, const float* __restrict__ src, float* __restrict__ dst, long long count) {
+  if (!c->snapshot) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
 struct NsfAdamArgs {
   float* params; float* m; float* v;
   const float* dW_part;      // [7][splits][128][128]
@@ -618,6 +776,76 @@ static size_t nsf_layout(int n_max, int planes, NsfLayout* L, void* base) {
 
 static int nsf_gemm(const himo_conv_desc& d, cudaStream_t stream) { return himo_conv2d_nhwc(&d, stream); }
 
+// h_1 = relu(W0 x + b0) on CUDA cores, then h_{l+1} = relu(W_l h_l + b_l), l = 1..7, on the tcgen05 GEMM
+static int nsf_forward_hidden(const NsfBufs& b, const NsfAdamArgs& ad, cudaStream_t stream) {
+  const int P = b.planes, n_pad = b.n_pad;
+  const float wscale = P == 2 ? 1.0f / kNsfWScale : 1.0f;
+  k_nsf_l0_fwd<<<min(n_pad / kL0Pts, kNumSMs * 8), 256, 0, stream>>>(b); HIMO_LAUNCH_RET();
+  for (int l = 1; l < kNsfLayers; ++l) {
+    himo_conv_desc g = {};
+    g.in = b.H[l]; g.in_planes = P; g.in_plane_stride = b.ps; g.H_in = n_pad / 128; g.W_in = 128;
+    g.Cin_total = 128; g.Cin = 128; g.wgt = ad.Wp[l]; g.bias = b.params + nsf_off_b(l); g.Cout = 128; g.ksize = 1;
+    g.stride = 1; g.out = b.H[l + 1]; g.out_planes = P; g.out_plane_stride = b.ps; g.Cout_total = 128; g.act = 4;
+    g.n_groups = 1; g.acc_scale = wscale; g.out_t = b.HT[l + 1]; g.out_t_plane_stride = b.ps; g.ld_t = n_pad;
+    g.stop_flag = &b.ctl->stop;
+    HIMO_RET(nsf_gemm(g, stream));
+  }
+  return HIMO_OK;
+}
+
+// From delta_8 in DL[0] / DLT[0]: for l = 7..1  dW_l = delta_{l+1}^T h_l (split-K over the points), db_l = row sums,
+// delta_l = (delta_{l+1} W_l) * relu'(h_l); then dW_0, db_0 from delta_1.  *cur_out: which DL / DLT pair holds delta_1.
+static int nsf_backward_hidden(const NsfBufs& b, const NsfAdamArgs& ad, float* dW_part, int splits, int k_split,
+                               int* cur_out, cudaStream_t stream) {
+  const int P = b.planes, n_pad = b.n_pad;
+  const float wscale = P == 2 ? 1.0f / kNsfWScale : 1.0f;
+  int cur = 0;
+  for (int l = kNsfLayers - 1; l >= 1; --l) {
+    himo_conv_desc g = {};
+    g.in = b.DLT[cur]; g.in_planes = P; g.in_plane_stride = b.ps; g.H_in = 1; g.W_in = 128;
+    g.Cin_total = n_pad; g.Cin = k_split; g.wgt = b.HT[l]; g.bias = nullptr; g.Cout = 128; g.ksize = 1; g.stride = 1;
+    g.out = dW_part + (size_t)(l - 1) * splits * 16384; g.out_fp32 = 1; g.out_planes = 1; g.Cout_total = 128;
+    g.n_groups = splits; g.cin_group_stride = k_split; g.cout_group_stride = 0; g.acc_scale = 1.f;
+    g.b_group_k_stride = k_split; g.out_group_pix_stride = 128; g.b_k_total = n_pad; g.stop_flag = &b.ctl->stop;
+    HIMO_RET(nsf_gemm(g, stream));
+    k_nsf_rowsum<<<dim3(128, kRowSplit), 128, 0, stream>>>(b, b.DLT[cur], b.rs_part, 0); HIMO_LAUNCH_RET();
+    k_nsf_rowsum_final<<<1, 128, 0, stream>>>(b, b.rs_part, b.gb + (l - 1) * 128, nullptr); HIMO_LAUNCH_RET();
+    himo_conv_desc q = {};
+    q.in = b.DL[cur]; q.in_planes = P; q.in_plane_stride = b.ps; q.H_in = n_pad / 128; q.W_in = 128;
+    q.Cin_total = 128; q.Cin = 128; q.wgt = ad.WpT[l]; q.bias = nullptr; q.Cout = 128; q.ksize = 1; q.stride = 1;
+    q.out = b.DL[cur ^ 1]; q.out_planes = P; q.out_plane_stride = b.ps; q.Cout_total = 128; q.act = 0;
+    q.n_groups = 1; q.acc_scale = wscale; q.out_t = b.DLT[cur ^ 1]; q.out_t_plane_stride = b.ps; q.ld_t = n_pad;
+    q.mask_src = b.H[l]; q.mask_plane_stride = b.ps; q.mask_planes = P; q.stop_flag = &b.ctl->stop;
+    HIMO_RET(nsf_gemm(q, stream));
+    cur ^= 1;
+  }
+  k_nsf_rowsum<<<dim3(128, kRowSplit), 128, 0, stream>>>(b, b.DLT[cur], b.rs_part, 1); HIMO_LAUNCH_RET();
+  k_nsf_rowsum_final<<<1, 128, 0, stream>>>(b, b.rs_part, b.gW0 + 384, b.gW0); HIMO_LAUNCH_RET();
+  if (cur_out) *cur_out = cur;
+  return HIMO_OK;
+}
+
+// Per-call view of a workspace: buffers, Adam arguments, split-K geometry for `n` points.
+struct NsfCall { NsfLayout L; NsfBufs b; NsfAdamArgs ad; int head_blocks, k_split, splits; };
+static int nsf_call_setup(void* workspace, size_t workspace_bytes, int n_max, int planes, int n, float lr, NsfCall* c) {
+  if (!workspace || (planes != 1 && planes != 2) || n <= 0 || n > n_max) return HIMO_ERR_ARG;
+  if (nsf_layout(n_max, planes, &c->L, workspace) > workspace_bytes) return HIMO_ERR_WORKSPACE;
+  const int n_pad = ceil_div(n, 128) * 128;
+  c->b = c->L.b;
+  c->b.n = n; c->b.n_pad = n_pad; c->b.planes = planes; c->b.ps = (long long)n_pad * 128;
+  int e = 0; while ((1 << e) < n) ++e;
+  c->b.grad_scale = (float)(1 << e);
+  c->head_blocks = ceil_div(n_pad, kHeadThreads);
+  c->k_split = 32 * ceil_div(n_pad, 32 * kNumSMs);
+  c->splits = ceil_div(n_pad, c->k_split);
+  c->ad = c->L.ad;
+  c->ad.params = c->b.params; c->ad.dW_part = c->L.dW_part; c->ad.splits = c->splits; c->ad.gb = c->b.gb;
+  c->ad.gW0 = c->b.gW0; c->ad.gb0 = c->b.gW0 + 384; c->ad.head_part = c->b.head_part; c->ad.head_blocks = c->head_blocks;
+  c->ad.planes = planes; c->ad.lr = lr; c->ad.beta1 = 0.9f; c->ad.beta2 = 0.999f; c->ad.eps = 1e-8f;
+  c->ad.inv_scale = 1.0f / c->b.grad_scale; c->ad.ctl = c->b.ctl;
+  return HIMO_OK;
+}
+
 }  // namespace himo
 
 using namespace himo;
@@ -715,45 +943,13 @@ extern "C" int himo_nsf_optimize(const himo_nsf_desc* d, void* stream_) {
   k_nsf_pack_weights<<<kNumSMs * 2, 256, 0, stream>>>(b.params, ad);
   HIMO_LAUNCH_RET();
 
-  const float wscale = P == 2 ? 1.0f / kNsfWScale : 1.0f;
   auto iteration = [&]() -> int {
-    k_nsf_l0_fwd<<<min(n_pad / kL0Pts, kNumSMs * 8), 256, 0, stream>>>(b); HIMO_LAUNCH_RET();
-    for (int l = 1; l < kNsfLayers; ++l) {                      // h_{l+1} = relu(W_l h_l + b_l)
-      himo_conv_desc g = {};
-      g.in = b.H[l]; g.in_planes = P; g.in_plane_stride = b.ps; g.H_in = n_pad / 128; g.W_in = 128;
-      g.Cin_total = 128; g.Cin = 128; g.wgt = ad.Wp[l]; g.bias = b.params + nsf_off_b(l); g.Cout = 128; g.ksize = 1;
-      g.stride = 1; g.out = b.H[l + 1]; g.out_planes = P; g.out_plane_stride = b.ps; g.Cout_total = 128; g.act = 4;
-      g.n_groups = 1; g.acc_scale = wscale; g.out_t = b.HT[l + 1]; g.out_t_plane_stride = b.ps; g.ld_t = n_pad;
-      g.stop_flag = &b.ctl->stop;
-      HIMO_RET(nsf_gemm(g, stream));
-    }
+    HIMO_RET(nsf_forward_hidden(b, ad, stream));
     k_nsf_head<<<head_blocks, kHeadThreads, 0, stream>>>(b, d->D, vol); HIMO_LAUNCH_RET();
     k_nsf_control<<<1, 32, 0, stream>>>(b, head_blocks, d->min_delta, d->patience); HIMO_LAUNCH_RET();
     k_nsf_snapshot<<<min(ceil_div(n, 256), kNumSMs * 4), 256, 0, stream>>>(b); HIMO_LAUNCH_RET();
     int cur = 0;
-    for (int l = kNsfLayers - 1; l >= 1; --l) {
-      // dW_l = delta_{l+1}^T h_l  (split-K over the points), db_l = row sums of delta_{l+1}^T
-      himo_conv_desc g = {};
-      g.in = b.DLT[cur]; g.in_planes = P; g.in_plane_stride = b.ps; g.H_in = 1; g.W_in = 128;
-      g.Cin_total = n_pad; g.Cin = k_split; g.wgt = b.HT[l]; g.bias = nullptr; g.Cout = 128; g.ksize = 1; g.stride = 1;
-      g.out = L.dW_part + (size_t)(l - 1) * splits * 16384; g.out_fp32 = 1; g.out_planes = 1; g.Cout_total = 128;
-      g.n_groups = splits; g.cin_group_stride = k_split; g.cout_group_stride = 0; g.acc_scale = 1.f;
-      g.b_group_k_stride = k_split; g.out_group_pix_stride = 128; g.b_k_total = n_pad; g.stop_flag = &b.ctl->stop;
-      HIMO_RET(nsf_gemm(g, stream));
-      k_nsf_rowsum<<<dim3(128, kRowSplit), 128, 0, stream>>>(b, b.DLT[cur], b.rs_part, 0); HIMO_LAUNCH_RET();
-      k_nsf_rowsum_final<<<1, 128, 0, stream>>>(b, b.rs_part, b.gb + (l - 1) * 128, nullptr); HIMO_LAUNCH_RET();
-      // delta_l = (delta_{l+1} W_l) * relu'(h_l)
-      himo_conv_desc q = {};
-      q.in = b.DL[cur]; q.in_planes = P; q.in_plane_stride = b.ps; q.H_in = n_pad / 128; q.W_in = 128;
-      q.Cin_total = 128; q.Cin = 128; q.wgt = ad.WpT[l]; q.bias = nullptr; q.Cout = 128; q.ksize = 1; q.stride = 1;
-      q.out = b.DL[cur ^ 1]; q.out_planes = P; q.out_plane_stride = b.ps; q.Cout_total = 128; q.act = 0;
-      q.n_groups = 1; q.acc_scale = wscale; q.out_t = b.DLT[cur ^ 1]; q.out_t_plane_stride = b.ps; q.ld_t = n_pad;
-      q.mask_src = b.H[l]; q.mask_plane_stride = b.ps; q.mask_planes = P; q.stop_flag = &b.ctl->stop;
-      HIMO_RET(nsf_gemm(q, stream));
-      cur ^= 1;
-    }
-    k_nsf_rowsum<<<dim3(128, kRowSplit), 128, 0, stream>>>(b, b.DLT[cur], b.rs_part, 1); HIMO_LAUNCH_RET();
-    k_nsf_rowsum_final<<<1, 128, 0, stream>>>(b, b.rs_part, b.gW0 + 384, b.gW0); HIMO_LAUNCH_RET();
+    HIMO_RET(nsf_backward_hidden(b, ad, L.dW_part, splits, k_split, &cur, stream));
     k_nsf_adam<<<kNumSMs * 2, 256, 0, stream>>>(ad); HIMO_LAUNCH_RET();
     return HIMO_OK;
   };
@@ -779,5 +975,110 @@ extern "C" int himo_nsf_optimize(const himo_nsf_desc* d, void* stream_) {
   if (d->iterations_out) *d->iterations_out = hc.iters;
   if (d->best_loss_out) *d->best_loss_out = hc.best_loss;
   if (d->last_loss_out) *d->last_loss_out = hc.loss;
+  return HIMO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- generic MLP C ABI
+// replaces: Neural_Prior.forward + autograd + torch.optim.Adam as NSFP uses them (OSF/src/models/nsfp.py:74-131,
+// basic/nsfp_module.py:7-47).  All state (parameters, Adam moments, activations, control block) lives in the
+// caller's workspace (himo_nsf_workspace_bytes); `ctl_workspace` (NULL = own) lets a second network follow the
+// control block -- iteration count and stop flag -- of the first (NSFP trains net and net_inv in lockstep).
+static NsfCtl* mlp_ctl(void* ctl_ws, int n_max, int planes, NsfCtl* own) {
+  if (!ctl_ws) return own;
+  NsfLayout o;
+  nsf_layout(n_max, planes, &o, ctl_ws);
+  return o.b.ctl;
+}
+
+extern "C" int himo_mlp_init(void* workspace, size_t workspace_bytes, int n_max, int planes, const float* init_params,
+                             void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NsfCall c;
+  if (!init_params) return HIMO_ERR_ARG;
+  HIMO_RET(nsf_call_setup(workspace, workspace_bytes, n_max, planes, 1, 0.f, &c));
+  HIMO_CUDA_RET(cudaMemcpyAsync(c.b.params, init_params, sizeof(float) * kNsfParams, cudaMemcpyDeviceToDevice, stream));
+  HIMO_CUDA_RET(cudaMemsetAsync(c.ad.m, 0, sizeof(float) * kNsfParams, stream));
+  HIMO_CUDA_RET(cudaMemsetAsync(c.ad.v, 0, sizeof(float) * kNsfParams, stream));
+  NsfCtl c0 = {};
+  c0.best_loss = INFINITY;
+  HIMO_CUDA_RET(cudaMemcpyAsync(c.b.ctl, &c0, sizeof(NsfCtl), cudaMemcpyHostToDevice, stream));
+  k_nsf_pack_weights<<<kNumSMs * 2, 256, 0, stream>>>(c.b.params, c.ad);
+  HIMO_LAUNCH_RET();
+  return HIMO_OK;
+}
+
+extern "C" int himo_mlp_forward(void* workspace, size_t workspace_bytes, int n_max, int planes, void* ctl_workspace,
+                                const float* x, int n, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NsfCall c;
+  if (!x || !out) return HIMO_ERR_ARG;
+  HIMO_RET(nsf_call_setup(workspace, workspace_bytes, n_max, planes, n, 0.f, &c));
+  c.b.ctl = mlp_ctl(ctl_workspace, n_max, planes, c.b.ctl);
+  k_nsf_pack_points<<<min(ceil_div(c.b.n_pad, 256), kNumSMs * 8), 256, 0, stream>>>(x, n, c.b.n_pad, (float4*)c.b.x4);
+  HIMO_LAUNCH_RET();
+  HIMO_RET(nsf_forward_hidden(c.b, c.ad, stream));
+  k_mlp_head_fwd<<<c.head_blocks, kHeadThreads, 0, stream>>>(c.b, out); HIMO_LAUNCH_RET();
+  return HIMO_OK;
+}
+
+extern "C" int himo_mlp_backward(void* workspace, size_t workspace_bytes, int n_max, int planes, void* ctl_workspace,
+                                 int n, const float* d_out, float* d_x, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NsfCall c;
+  if (!d_out) return HIMO_ERR_ARG;
+  HIMO_RET(nsf_call_setup(workspace, workspace_bytes, n_max, planes, n, 0.f, &c));
+  c.b.ctl = mlp_ctl(ctl_workspace, n_max, planes, c.b.ctl);
+  k_mlp_head_bwd<<<c.head_blocks, kHeadThreads, 0, stream>>>(c.b, d_out); HIMO_LAUNCH_RET();
+  int cur = 0;
+  HIMO_RET(nsf_backward_hidden(c.b, c.ad, c.L.dW_part, c.splits, c.k_split, &cur, stream));
+  if (d_x) {
+    k_mlp_dx<<<ceil_div(n, 128), 128, 0, stream>>>(c.b, c.b.DL[cur], c.ad.inv_scale, d_x);
+    HIMO_LAUNCH_RET();
+  }
+  return HIMO_OK;
+}
+
+// torch.optim.Adam.step for this network with the gradients of the last himo_mlp_backward; the step number is the
+// control block's iteration count (himo_mlp_control increments it once per loss evaluation, like the reference's loop).
+extern "C" int himo_mlp_adam_step(void* workspace, size_t workspace_bytes, int n_max, int planes, void* ctl_workspace,
+                                  int n, float lr, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NsfCall c;
+  HIMO_RET(nsf_call_setup(workspace, workspace_bytes, n_max, planes, n, lr, &c));
+  c.ad.ctl = mlp_ctl(ctl_workspace, n_max, planes, c.b.ctl);
+  k_nsf_adam<<<kNumSMs * 2, 256, 0, stream>>>(c.ad); HIMO_LAUNCH_RET();
+  return HIMO_OK;
+}
+
+// One loss evaluation of the optimisation loop: best-loss / early-stopping state machine on the device, then the
+// best-output snapshot (`out` [count] floats -> `best_out`, both device) if this loss is the best so far.
+extern "C" int himo_mlp_control(void* workspace, size_t workspace_bytes, int n_max, int planes, const float* loss_dev,
+                                float min_delta, int patience, const float* out, float* best_out, long long count,
+                                void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NsfCall c;
+  if (!loss_dev) return HIMO_ERR_ARG;
+  HIMO_RET(nsf_call_setup(workspace, workspace_bytes, n_max, planes, 1, 0.f, &c));
+  k_mlp_control<<<1, 32, 0, stream>>>(c.b.ctl, loss_dev, min_delta, patience); HIMO_LAUNCH_RET();
+  if (out && best_out && count > 0) {
+    k_mlp_snapshot<<<(int)min((long long)kNumSMs * 4, ceil_div_ll(count, 256)), 256, 0, stream>>>(c.b.ctl, out, best_out, count);
+    HIMO_LAUNCH_RET();
+  }
+  return HIMO_OK;
+}
+
+// Blocking read of the control block: state[0] = stop, [1] = iterations, [2] = best loss, [3] = last loss.
+extern "C" int himo_mlp_read_state(void* workspace, size_t workspace_bytes, int n_max, int planes, float* state_host,
+                                   float* params_out, float* exp_avg_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NsfCall c;
+  if (!state_host) return HIMO_ERR_ARG;
+  HIMO_RET(nsf_call_setup(workspace, workspace_bytes, n_max, planes, 1, 0.f, &c));
+  NsfCtl hc;
+  HIMO_CUDA_RET(cudaMemcpyAsync(&hc, c.b.ctl, sizeof(NsfCtl), cudaMemcpyDeviceToHost, stream));
+  if (params_out) HIMO_CUDA_RET(cudaMemcpyAsync(params_out, c.b.params, sizeof(float) * kNsfParams, cudaMemcpyDeviceToDevice, stream));
+  if (exp_avg_out) HIMO_CUDA_RET(cudaMemcpyAsync(exp_avg_out, c.ad.m, sizeof(float) * kNsfParams, cudaMemcpyDeviceToDevice, stream));
+  HIMO_CUDA_RET(cudaStreamSynchronize(stream));
+  state_host[0] = (float)hc.stop; state_host[1] = (float)hc.iters; state_host[2] = hc.best_loss; state_host[3] = hc.loss;
   return HIMO_OK;
 }

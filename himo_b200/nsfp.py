@@ -2,21 +2,22 @@
 
 Per frame pair two coordinate MLPs are fitted at run time: `net` maps the ego-compensated pc0 to a flow, `net_inv` maps
 the displaced points back, and the loss is the NSFP-truncated bidirectional Chamfer distance of both (nsfp.py:48-72).
-What this module puts on our kernels is the part that dominates the reference's iteration -- four exact 1-NN searches
-and their gradient scatter per iteration, served by `himo_b200.chamfer3d` with the truncation radius (sqrt(2) m) pruning
-the search, where the reference's chamfer3D kernel is O(N*M) brute force.  The 8x128 MLP forward/backward and Adam of
-this path still go through torch (cuBLAS, `torch.optim.Adam`): library code, stated as such in DESIGN.md; FastNSF's own
-tcgen05 MLP kernels (csrc/nsf.cu) are specialised to its distance-volume loss and are not reused here yet.
+Everything heavy runs on the library's own kernels: the two 8x128 MLPs forward / backward and their Adam steps
+(`himo_b200.mlp.PriorMLP` = himo_mlp_forward / _backward / _adam_step: tcgen05 GEMMs with fp32-class split-fp16 operands,
+the same kernels FastNSF uses), the four exact 1-NN searches and their gradient scatter per iteration
+(`himo_b200.chamfer3d`, the truncation radius sqrt(2) m pruning the search where the reference's kernel is O(N*M)).
+torch only glues them (autograd bookkeeping and a handful of element-wise ops on [N,3] tensors).  CUDA only.
 
-The control flow keeps the reference's meaning: best flow so far under `loss <= best`, early stopping on
-`loss < best - min_delta` in float32 with `patience` bad iterations, a NaN loss stops at once, at least one iteration.
+The control flow keeps the reference's meaning -- best flow so far under `loss <= best`, early stopping on
+`loss < best - min_delta` in float32 with `patience` bad iterations, a NaN loss stops at once, at least one iteration --
+but runs on the DEVICE (himo_mlp_control): the reference reads the loss back every iteration (`loss.item()`, nsfp.py:
+108-112); here the host polls a stop flag every `poll_iters` iterations and a stopped network's kernels are no-ops.
 Initial weights: like the reference, a fresh default-initialised `Linear` stack drawn from the global torch CPU RNG
 (nsfp.py:78-81, so `torch.manual_seed(s)` before the call reproduces the reference's network), `net_inv` an exact copy;
 `init_state_dict` (a reference `Neural_Prior.state_dict()`) overrides it.
 """
 from __future__ import annotations
 
-import copy
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -105,36 +106,43 @@ class NSFP:
                 (pc[:, 2] >= r[2]) & (pc[:, 2] <= r[5]))
         return pc[mask], mask
 
-    def optimize(self, pc0: torch.Tensor, pc1: torch.Tensor, init_state_dict: Optional[Dict] = None) -> Dict:
-        """pc0 (ego-compensated) / pc1: [N,3] f32, already range-limited.  -> {'loss', 'flow', 'iterations'}."""
+    def optimize(self, pc0: torch.Tensor, pc1: torch.Tensor, init_state_dict: Optional[Dict] = None,
+                 poll_iters: int = 8) -> Dict:
+        """pc0 (ego-compensated) / pc1: [N,3] f32 CUDA, already range-limited.  -> {'loss', 'flow', 'iterations'}."""
+        from . import _lib
+        from .mlp import PriorMLP
+        _lib.require_cuda(pc0, "pc0")
+        _lib.require_cuda(pc1, "pc1")
         ch = self._ch()
         dev = pc0.device
-        net = _Prior(filter_size=self.filter_size, act_fn=self.act_fn, layer_size=self.layer_size)
-        if init_state_dict is not None:
-            net.load_state_dict({k: torch.as_tensor(v) for k, v in init_state_dict.items()}, strict=True)
-        net = net.to(dev).train()
-        net_inv = copy.deepcopy(net)
-        opt = torch.optim.Adam([{"params": net.parameters()}, {"params": net_inv.parameters()}], lr=self.lr, weight_decay=0)
-        stop = _EarlyStop(self.early_patience, self.min_delta)
+        if init_state_dict is None:      # the reference's fresh default-initialised network, from the global torch CPU RNG
+            init_state_dict = _Prior(filter_size=self.filter_size, act_fn=self.act_fn, layer_size=self.layer_size).state_dict()
+        if self.filter_size != 128 or self.layer_size != 8 or self.act_fn != "relu":
+            raise NotImplementedError("himo_b200.NSFP implements the 8x128 ReLU prior of conf/model/nsfp.yaml")
         pc0 = pc0.detach().contiguous()
         pc1 = pc1.detach().contiguous()
-        best_loss, best_flow, iters = float("inf"), None, 0
+        n = pc0.shape[0]
+        net = PriorMLP(init_state_dict, n, dev)
+        net_inv = PriorMLP(init_state_dict, n, dev, follow=net)          # copy.deepcopy(net), nsfp.py:82
+        best_flow = torch.zeros_like(pc0)
+        state = {"stop": False, "iterations": 0}
         with torch.inference_mode(False), torch.enable_grad():
-            for _ in range(self.iteration_num):
-                opt.zero_grad()
+            for it in range(self.iteration_num):
                 flow = net(pc0)
                 moved = pc0 + flow
                 back = moved - net_inv(moved)
                 loss = ch.truncated_dis(moved, pc1, NSFP_TRUNCATE_SQ) + ch.truncated_dis(back, pc0, NSFP_TRUNCATE_SQ)
-                lv = float(loss.detach())
-                iters += 1
-                if lv <= best_loss:
-                    best_loss, best_flow = lv, flow.detach()
-                if stop.step(lv) and best_flow is not None:
-                    break
+                # nsfp.py:104-113 on the device: count the iteration, keep the best flow, EarlyStopping.step
+                net.control(loss, self.min_delta, self.early_patience, out=flow, best_out=best_flow)
                 loss.backward()
-                opt.step()
-        if best_flow is None:
+                net.adam_step(self.lr)
+                net_inv.adam_step(self.lr)
+                if (it + 1) % max(1, poll_iters) == 0 or it + 1 == self.iteration_num:
+                    state = net.read_state()
+                    if state["stop"]:
+                        break
+        best_loss, iters = state["best_loss"], state["iterations"]
+        if not np.isfinite(best_loss):
             raise RuntimeError("NSFP: the loss was never finite")        # the reference dies on model_res['flow'] here
         self.last_info = {"loss": best_loss, "iterations": iters}
         return {"loss": best_loss, "flow": best_flow, "iterations": iters}

@@ -351,6 +351,40 @@ int himo_nsf_dt_build(const float* pc1, int n1, const float* lo, const int32_t* 
                       float* D, void* stream);
 int himo_nsf_optimize(const himo_nsf_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * H3 / (f)1  the same 3 -> 128 x 8 -> 3 ReLU prior with the loss OUTSIDE the library (NSFP)
+ * replaces: Neural_Prior.forward, its autograd backward and torch.optim.Adam.step as NSFP.optimize uses them
+ *           (OSF/src/models/nsfp.py:74-131, OSF/src/models/basic/nsfp_module.py:7-47), plus the loop's
+ *           best-flow / EarlyStopping bookkeeping (nsfp.py:104-113, nsfp_module.py:60-82) on the device.
+ * All state -- parameters (reference state_dict order, HIMO_NSF_NUM_PARAMS floats), Adam moments, activations,
+ * control block -- lives in the caller's workspace of himo_nsf_workspace_bytes(n_max, planes) bytes; every call
+ * re-derives its views from (workspace, n_max, planes).  `ctl_workspace` (NULL = own) makes a network follow the
+ * control block (iteration count, stop flag) of another one: NSFP steps `net` and `net_inv` in lockstep.
+ *   himo_mlp_init        parameters <- init_params (DEVICE), moments <- 0, control block reset
+ *   himo_mlp_forward     out[n,3] = MLP(x[n,3]); keeps the activations for the backward pass
+ *   himo_mlp_backward    d_out[n,3] = d loss / d out  ->  parameter gradients (in the workspace) and, if d_x != NULL,
+ *                        d_x[n,3] = d loss / d x
+ *   himo_mlp_adam_step   Adam(lr, betas 0.9 / 0.999, eps 1e-8, no weight decay) with those gradients; the step
+ *                        number is the control block's iteration count
+ *   himo_mlp_control     one loss evaluation: iteration count += 1; if loss <= best: best <- loss and
+ *                        best_out[count] <- out[count]; EarlyStopping.step(loss) -> stop flag (kernels of a stopped
+ *                        network are no-ops).  loss_dev: DEVICE float.
+ *   himo_mlp_read_state  blocking: state_host[4] = {stop, iterations, best loss, last loss}; optional DEVICE copies
+ *                        of the parameters and of Adam's first moment
+ */
+int himo_mlp_init(void* workspace, size_t workspace_bytes, int n_max, int planes, const float* init_params,
+                  void* stream);
+int himo_mlp_forward(void* workspace, size_t workspace_bytes, int n_max, int planes, void* ctl_workspace,
+                     const float* x, int n, float* out, void* stream);
+int himo_mlp_backward(void* workspace, size_t workspace_bytes, int n_max, int planes, void* ctl_workspace, int n,
+                      const float* d_out, float* d_x, void* stream);
+int himo_mlp_adam_step(void* workspace, size_t workspace_bytes, int n_max, int planes, void* ctl_workspace, int n,
+                       float lr, void* stream);
+int himo_mlp_control(void* workspace, size_t workspace_bytes, int n_max, int planes, const float* loss_dev,
+                     float min_delta, int patience, const float* out, float* best_out, long long count, void* stream);
+int himo_mlp_read_state(void* workspace, size_t workspace_bytes, int n_max, int planes, float* state_host,
+                        float* params_out, float* exp_avg_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,3 +51,60 @@ def test_nsfp_loss_decreases_and_early_stop():
     longer = nsfp.NSFP(itr_num=45, early_patience=30)
     longer(_batch(z), init_state_dicts=[golden_state_dict(z)])
     assert longer.last_info["iterations"] > 6 and longer.last_info["loss"] < 0.1515
+
+
+def test_prior_mlp_forward_backward_match_torch_autograd():
+    """himo_b200.mlp.PriorMLP (himo_mlp_forward / _backward / _adam_step) against torch autograd on the same network:
+    output <= 1e-5, d loss / d input and the full parameter gradient (read back through Adam's first moment after one
+    step: exp_avg = 0.1 * grad) cos > 1 - 1e-6."""
+    from himo_b200 import mlp
+    from himo_b200.fastnsf import flatten_params
+    torch.manual_seed(3)
+    ref = nsfp._Prior()
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    n = 5000
+    x = (torch.rand(n, 3) * 40 - 20)
+    w = torch.randn(n, 3) / n
+    xr = x.clone().requires_grad_(True)
+    out_ref = ref(xr)
+    (out_ref * w).sum().backward()
+    g_ref = flatten_params({k: p.grad for k, p in ref.named_parameters()} | {})
+    net = mlp.PriorMLP(sd, n, "cuda")
+    xc = x.cuda().requires_grad_(True)
+    out = net(xc)
+    assert (out.detach().cpu() - out_ref.detach()).abs().max().item() <= 1e-5 * max(1.0, out_ref.abs().max().item())
+    loss = (out * w.cuda()).sum()
+    net.control(loss, 5e-5, 30)
+    loss.backward()
+    cos = torch.nn.functional.cosine_similarity(xc.grad.cpu().flatten(), xr.grad.flatten(), dim=0).item()
+    assert cos > 1 - 1e-6, cos
+    assert (xc.grad.cpu() - xr.grad).abs().max().item() <= 1e-4 * xr.grad.abs().max().item()
+    net.adam_step(8e-3)
+    st = net.read_state(with_params=True)
+    g = st["exp_avg"].cpu() / 0.1
+    cos = torch.nn.functional.cosine_similarity(g, g_ref, dim=0).item()
+    assert cos > 1 - 1e-6, cos
+    assert (g - g_ref).abs().max().item() <= 1e-4 * g_ref.abs().max().item()
+    # one Adam step from zero moments moves every parameter by lr * sign(grad) (bias-corrected), up to eps
+    p0 = flatten_params(sd)
+    step = st["params"].cpu() - p0
+    big = g_ref.abs() > 1e-3 * g_ref.abs().max()      # eps = 1e-8 matters for the tiniest gradients
+    assert torch.allclose(step[big], -8e-3 * torch.sign(g_ref[big]), atol=1e-5)
+
+
+def test_mlp_control_is_the_reference_early_stopping_rule():
+    from himo_b200 import mlp
+    sd = nsfp._Prior().state_dict()
+    losses = [1.0, 0.95, 0.97, 0.96, 0.90, 0.91, 0.92, 0.93, 0.5]
+    net = mlp.PriorMLP(sd, 4096, "cuda")
+    es = nsfp._EarlyStop(patience=3, min_delta=0.02)
+    best, n_iter = float("inf"), 0
+    for v in losses:
+        n_iter += 1
+        best = min(best, v)
+        if es.step(v):
+            break
+    for v in losses:
+        net.control(torch.tensor(v, device="cuda"), 0.02, 3)
+    st = net.read_state()
+    assert st["stop"] and st["iterations"] == n_iter and st["best_loss"] == pytest.approx(best)
