@@ -10,6 +10,7 @@
 // (dW, split-K) on the tcgen05 GEMM kernel of conv.cu with ReLU / ReLU-mask / transposed stores fused into
 // its epilogue; loss, best-flow snapshot, early stopping and Adam live in a device control block; the
 // host only polls a stop flag every few iterations.
+#include <cudaTypedefs.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -163,22 +164,26 @@ k_nsf_dt_pass(float* __restrict__ d, int n0, int n1, int n2, int axis, int dir, 
 }
 
 // ------------------------------------------------------------------------------ MLP pieces outside the GEMMs
+// Activations h_l and back-propagated deltas are kept ROW-MAJOR only ([points][128 features], split planes).  The
+// forward and dX GEMMs read them as K-major operands (K = features); the weight-gradient kernel k_nsf_dw reads the
+// SAME tiles as MN-major operands (M / N = features, K = points) -- the 64-byte-swizzled tile TMA writes is both at
+// once (scripts/exp/mn_major.cu, profiles/r02_exp_mn_major_operands.txt).  Round 1 kept a transposed copy of every
+// tensor for the dW GEMMs: 2-byte scattered stores in 15 epilogues and twice the activation traffic.
 struct NsfBufs {
   const float4* x4;                // [n_pad] source points (xyz, 0)
+  __nv_bfloat16* x16;              // [planes][n_pad][32]: (x, y, z, 1, 0...) per point, 0 rows beyond n -- the "h_0" of k_nsf_dw
   int n, n_pad;
   int planes;
-  long long ps;                    // plane stride of the [n_pad][128] / [128][n_pad] tensors
-  __nv_bfloat16* H[kNsfLayers + 1];    // H[l], l = 1..8: activations row-major planes
-  __nv_bfloat16* HT[kNsfLayers + 1];   // transposed planes
-  __nv_bfloat16* DL[2];
-  __nv_bfloat16* DLT[2];
+  long long ps;                    // plane stride of the [n_pad][128] tensors
+  __nv_bfloat16* H[kNsfLayers + 1];    // H[l], l = 1..8: activations
+  __nv_bfloat16* DL[kNsfLayers + 1];   // DL[l], l = 1..8: delta_l = d loss / d (pre-activation of h_l), scaled by grad_scale
   float* params;                   // master fp32 parameters, reference layout
   float* flow;                     // [n_pad][4]
   float* best_flow;                // [n_pad][4]
   float* head_part;                // [head_blocks][kHeadPart]
   float* gW0;                      // [128][3] + [128] bias
   float* gb;                       // [7][128] bias grads of layers 1..7 (scaled)
-  float* rs_part;                  // [kRowSplit][4][128] row-sum partials
+  float* small_part;               // [8][splits][128][4]: per split (delta_{l+1}^T x, delta_{l+1}^T 1)
   NsfCtl* ctl;
   float grad_scale;                // power of two S; every backward tensor carries S/N instead of 1/N
 };
@@ -195,99 +200,165 @@ __host__ __device__ inline int nsf_off_b(int l) {
 }
 constexpr int kNsfParams = 128 * 3 + 128 + 7 * (128 * 128 + 128) + 3 * 128 + 3;   // 116483
 
-// layer 0: h1 = relu(W0 x + b0), K = 3 -> plain FMAs; writes row-major and transposed planes.
-// One block = 64 points x 128 features.  Phase A: a thread owns 32 consecutive features of one point (64-byte
-// row-major stores per plane) and parks the 16-bit planes in shared memory; phase B: a thread owns 32 consecutive
-// points of one feature and writes the transposed planes with 16-byte stores (the element-wise version issued
-// 2-byte stores n_pad elements apart: 235 us per iteration at 100 k points).
+// layer 0: h1 = relu(W0 x + b0), K = 3 -> plain FMAs.  A thread owns 32 consecutive features of one point
+// (64-byte row-major stores per plane).
 constexpr int kL0Pts = 64;
 __global__ void __launch_bounds__(256)
 k_nsf_l0_fwd(NsfBufs b) {
   if (b.ctl->stop) return;
-  __shared__ __align__(16) unsigned short s_pl[2][128][kL0Pts + 8];
-  const float* W = b.params + nsf_off_w(0);
-  const float* bias = b.params + nsf_off_b(0);
+  __shared__ float sW[384], sB[128];
+  for (int t = threadIdx.x; t < 384; t += 256) sW[t] = b.params[nsf_off_w(0) + t];
+  for (int t = threadIdx.x; t < 128; t += 256) sB[t] = b.params[nsf_off_b(0) + t];
+  __syncthreads();
   const bool split = b.planes == 2;
   for (long long base = (long long)blockIdx.x * kL0Pts; base < b.n_pad; base += (long long)gridDim.x * kL0Pts) {
-    {
-      const int pi = threadIdx.x >> 2, j0 = (threadIdx.x & 3) * 32;
-      const long long i = base + pi;
-      const float4 p = b.x4[i];
-      uint32_t hi[16], lo[16];
+    const int pi = threadIdx.x >> 2, j0 = (threadIdx.x & 3) * 32;
+    const long long i = base + pi;
+    const float4 p = b.x4[i];
+    uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        float v[2];
+    for (int k = 0; k < 16; ++k) {
+      float v[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int j = j0 + 2 * k + u;
-          float t = __ldg(W + j * 3) * p.x;
-          t = fmaf(__ldg(W + j * 3 + 1), p.y, t);
-          t = fmaf(__ldg(W + j * 3 + 2), p.z, t);
-          v[u] = fmaxf(t + __ldg(bias + j), 0.f);
-        }
-        umma::pack_split2(v[0], v[1], split, hi[k], lo[k]);
-        s_pl[0][j0 + 2 * k][pi] = (unsigned short)(hi[k] & 0xffffu);
-        s_pl[0][j0 + 2 * k + 1][pi] = (unsigned short)(hi[k] >> 16);
-        if (split) {
-          s_pl[1][j0 + 2 * k][pi] = (unsigned short)(lo[k] & 0xffffu);
-          s_pl[1][j0 + 2 * k + 1][pi] = (unsigned short)(lo[k] >> 16);
-        }
+      for (int u = 0; u < 2; ++u) {
+        const int j = j0 + 2 * k + u;
+        float t = sW[j * 3] * p.x;
+        t = fmaf(sW[j * 3 + 1], p.y, t);
+        t = fmaf(sW[j * 3 + 2], p.z, t);
+        v[u] = fmaxf(t + sB[j], 0.f);
       }
-      uint4* d0 = (uint4*)(b.H[1] + i * 128 + j0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) d0[k] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
-      if (split) {
-        uint4* d1 = (uint4*)(b.H[1] + b.ps + i * 128 + j0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) d1[k] = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
-      }
+      umma::pack_split2(v[0], v[1], split, hi[k], lo[k]);
     }
-    __syncthreads();
-    {
-      const int f = threadIdx.x >> 1, p0 = (threadIdx.x & 1) * 32;
-      for (int pl = 0; pl < b.planes; ++pl) {
-        const uint4* src = (const uint4*)&s_pl[pl][f][p0];
-        uint4* dst = (uint4*)(b.HT[1] + (long long)pl * b.ps + (long long)f * b.n_pad + base + p0);
+    uint4* d0 = (uint4*)(b.H[1] + i * 128 + j0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dst[k] = src[k];
-      }
+    for (int k = 0; k < 4; ++k) d0[k] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+    if (split) {
+      uint4* d1 = (uint4*)(b.H[1] + b.ps + i * 128 + j0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d1[k] = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
     }
-    __syncthreads();
   }
 }
 
-__device__ __forceinline__ float load_split(const __nv_bfloat16* p, long long ps, int planes) {
+// 8 consecutive features of one point from a row-major split-plane tensor
+__device__ __forceinline__ void load_split8(const __nv_bfloat16* p, long long ps, int planes, float v[8]) {
+  const uint4 a = *(const uint4*)p;
+  const uint32_t aa[4] = {a.x, a.y, a.z, a.w};
   if (planes == 2) {
-    const __half* h = reinterpret_cast<const __half*>(p);
-    return __half2float(h[0]) + __half2float(h[ps]);
+    const uint4 l = *(const uint4*)(p + ps);
+    const uint32_t ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&aa[k]));
+      const float2 l2 = __half22float2(*reinterpret_cast<const __half2*>(&ll[k]));
+      v[2 * k] = h2.x + l2.x; v[2 * k + 1] = h2.y + l2.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[2 * k] = __uint_as_float(aa[k] << 16); v[2 * k + 1] = __uint_as_float(aa[k] & 0xffff0000u); }
   }
-  return __bfloat162float(p[0]);
 }
 
 constexpr int kHeadThreads = 128;
 constexpr int kHeadPart = 3 * 128 + 3 + 1;   // dW8, db8, loss
 
-// Output layer + loss + its backward, one thread per point:
-//   flow = W8 h8 + b8; Y = x + flow; loss_i = trilinear D(Y); dflow = grad_Y D * (S/N)
-//   dh8 = (dflow . W8) * relu'(h8); per-block partial sums of dW8, db8 and the loss.
+// output layer of point i: flow = W8 h8 + b8 (W8 staged in shared memory)
+__device__ __forceinline__ void head_flow(const NsfBufs& b, const float* sW8, int i, float f[3]) {
+  const float* b8 = b.params + nsf_off_b(8);
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+  const __nv_bfloat16* h8 = b.H[8] + (long long)i * 128;
+  for (int j0 = 0; j0 < 128; j0 += 8) {
+    float h[8];
+    load_split8(h8 + j0, b.ps, b.planes, h);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      f0 = fmaf(sW8[j0 + u], h[u], f0);
+      f1 = fmaf(sW8[128 + j0 + u], h[u], f1);
+      f2 = fmaf(sW8[256 + j0 + u], h[u], f2);
+    }
+  }
+  f[0] = f0 + __ldg(b8); f[1] = f1 + __ldg(b8 + 1); f[2] = f2 + __ldg(b8 + 2);
+}
+
+// backward through the output layer and the ReLU of h8: delta_8 = (d W8) * relu'(h8) -> DL[8]; per-block partial sums
+// of dW8 [3][128], db8 [3] and `extra` (the loss for FastNSF) in head_part (fixed shuffle trees => deterministic)
+__device__ __forceinline__ void head_backward(const NsfBufs& b, const float* sW8, int i, float d0, float d1, float d2,
+                                              float extra, float (*red_w)[3][128], float (*red)[4]) {
+  float* part = b.head_part + (size_t)blockIdx.x * kHeadPart;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool in_pad = i < b.n_pad;
+  const bool split = b.planes == 2;
+  const __nv_bfloat16* h8 = b.H[8] + (long long)i * 128;
+  for (int j0 = 0; j0 < 128; j0 += 8) {
+    float h[8], dhv[8];
+    if (in_pad) load_split8(h8 + j0, b.ps, b.planes, h);
+    else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) h[u] = 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u;
+      float dh = fmaf(d2, sW8[256 + j], fmaf(d1, sW8[128 + j], d0 * sW8[j]));
+      if (!(h[u] > 0.f)) dh = 0.f;
+      dhv[u] = dh;
+      float a0 = d0 * h[u], a1 = d1 * h[u], a2 = d2 * h[u];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, sft);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, sft);
+      }
+      if (lane == 0) { red_w[warp][0][j] = a0; red_w[warp][1][j] = a1; red_w[warp][2][j] = a2; }
+    }
+    if (in_pad) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) umma::pack_split2(dhv[2 * u], dhv[2 * u + 1], split, hi[u], lo[u]);
+      *(uint4*)(b.DL[8] + (long long)i * 128 + j0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (split) *(uint4*)(b.DL[8] + b.ps + (long long)i * 128 + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 384; t += kHeadThreads) {
+    const int k = t >> 7, j = t & 127;
+    float sacc = 0.f;
+    for (int wv = 0; wv < kHeadThreads / 32; ++wv) sacc += red_w[wv][k][j];
+    part[k * 128 + j] = sacc;
+  }
+  float a0 = d0, a1 = d1, a2 = d2, a3 = extra;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, s);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, s);
+    a3 += __shfl_xor_sync(0xffffffffu, a3, s);
+  }
+  if (lane == 0) { red[warp][0] = a0; red[warp][1] = a1; red[warp][2] = a2; red[warp][3] = a3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+    for (int wv = 0; wv < kHeadThreads / 32; ++wv) s += red[wv][threadIdx.x];
+    part[384 + threadIdx.x] = s;
+  }
+}
+
+// FastNSF head: output layer + loss + its backward, one thread per point:
+//   flow = W8 h8 + b8; Y = x + flow; loss_i = trilinear D(Y); dflow = grad_Y D * (S/N); delta_8, dW8, db8, loss partials.
 __global__ void __launch_bounds__(kHeadThreads)
 k_nsf_head(NsfBufs b, const float* __restrict__ D, NsfVol vol) {
   if (b.ctl->stop) return;
   __shared__ float red[kHeadThreads / 32][4];
-  const float* W8 = b.params + nsf_off_w(8);
-  const float* b8 = b.params + nsf_off_b(8);
+  __shared__ float red_w[kHeadThreads / 32][3][128];
+  __shared__ float sW8[384];
+  for (int t = threadIdx.x; t < 384; t += kHeadThreads) sW8[t] = b.params[nsf_off_w(8) + t];
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < b.n;
   const int ii = live ? i : 0;
-  const __nv_bfloat16* hT = b.HT[8];
-  float f0 = 0.f, f1 = 0.f, f2 = 0.f;
-  for (int j = 0; j < 128; ++j) {
-    const float h = load_split(hT + (long long)j * b.n_pad + ii, b.ps, b.planes);
-    f0 = fmaf(__ldg(W8 + j), h, f0);
-    f1 = fmaf(__ldg(W8 + 128 + j), h, f1);
-    f2 = fmaf(__ldg(W8 + 256 + j), h, f2);
-  }
-  f0 += __ldg(b8); f1 += __ldg(b8 + 1); f2 += __ldg(b8 + 2);
+  float f[3];
+  head_flow(b, sW8, ii, f);
+  const float f0 = f[0], f1 = f[1], f2 = f[2];
   const float4 x = b.x4[ii];
   const float Y[3] = {x.x + f0, x.y + f1, x.z + f2};
   // DT.torch_bilinear_distance (fastnsf.py:59-80) followed by grid_sample's own un-normalisation
@@ -322,66 +393,10 @@ k_nsf_head(NsfBufs b, const float* __restrict__ D, NsfVol vol) {
   }
   // d ix / dY = (sz/2) * (2/sz) * gf * [inside] = gf * [inside]
   const float sN = b.grad_scale / (float)b.n;
-  float d0 = live ? gx * pass[0] * sN : 0.f, d1 = live ? gy * pass[1] * sN : 0.f, d2 = live ? gz * pass[2] * sN : 0.f;
+  const float d0 = live ? gx * pass[0] * sN : 0.f, d1 = live ? gy * pass[1] * sN : 0.f, d2 = live ? gz * pass[2] * sN : 0.f;
   if (!live) val = 0.f;
   if (live) *(float4*)(b.flow + 4 * (size_t)i) = make_float4(f0, f1, f2, val);
-  // backward through the output layer + ReLU mask of h8
-  float* part = b.head_part + (size_t)blockIdx.x * kHeadPart;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __shared__ float red_w[kHeadThreads / 32][3][128];
-  const bool in_pad = i < b.n_pad;
-  const bool split = b.planes == 2;
-  for (int j0 = 0; j0 < 128; j0 += 8) {
-    uint32_t hi[4], lo[4];
-    float dhv[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u;
-      const float h = in_pad ? load_split(hT + (long long)j * b.n_pad + i, b.ps, b.planes) : 0.f;
-      float dh = fmaf(d2, __ldg(W8 + 256 + j), fmaf(d1, __ldg(W8 + 128 + j), d0 * __ldg(W8 + j)));
-      if (!(h > 0.f)) dh = 0.f;
-      dhv[u] = dh;
-      if (in_pad) umma::store_split(b.DLT[0] + (long long)j * b.n_pad + i, b.ps, b.planes, dh);   // lanes = consecutive points
-      // dW8[k][j] partial = sum over the block's points of d_k * h_j (fixed shuffle tree => deterministic)
-      float a0 = d0 * h, a1 = d1 * h, a2 = d2 * h;
-#pragma unroll
-      for (int sft = 16; sft > 0; sft >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, sft);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
-        a2 += __shfl_xor_sync(0xffffffffu, a2, sft);
-      }
-      if (lane == 0) { red_w[warp][0][j] = a0; red_w[warp][1][j] = a1; red_w[warp][2][j] = a2; }
-    }
-    if (in_pad) {   // row-major copy: 8 features = one 16-byte store per plane
-#pragma unroll
-      for (int u = 0; u < 4; ++u) umma::pack_split2(dhv[2 * u], dhv[2 * u + 1], split, hi[u], lo[u]);
-      *(uint4*)(b.DL[0] + (long long)i * 128 + j0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      if (split) *(uint4*)(b.DL[0] + b.ps + (long long)i * 128 + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < 384; t += kHeadThreads) {
-    const int k = t >> 7, j = t & 127;
-    float sacc = 0.f;
-    for (int wv = 0; wv < kHeadThreads / 32; ++wv) sacc += red_w[wv][k][j];
-    part[k * 128 + j] = sacc;
-  }
-  __syncthreads();
-  float a0 = d0, a1 = d1, a2 = d2, a3 = val;
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, s);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, s);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, s);
-    a3 += __shfl_xor_sync(0xffffffffu, a3, s);
-  }
-  if (lane == 0) { red[warp][0] = a0; red[warp][1] = a1; red[warp][2] = a2; red[warp][3] = a3; }
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    float s = 0.f;
-    for (int wv = 0; wv < kHeadThreads / 32; ++wv) s += red[wv][threadIdx.x];
-    part[384 + threadIdx.x] = s;
-  }
+  head_backward(b, sW8, i, d0, d1, d2, val, red_w, red);
 }
 
 // loss reduction + best-flow bookkeeping + EarlyStopping.step (nsfp_module.py:65-82), single thread.
@@ -420,71 +435,188 @@ k_nsf_snapshot(NsfBufs b) {
     *(float4*)(b.best_flow + 4 * (size_t)i) = *(const float4*)(b.flow + 4 * (size_t)i);
 }
 
-// bias gradient of layer l (1..7) = row sums of delta_{l+1}^T; for layer 0 also dW0 = delta_1^T x.
-// grid (128 features, kRowSplit point ranges): 16-byte loads of 8 consecutive points per plane, fixed-order
-// reductions (deterministic); k_nsf_rowsum_final adds the kRowSplit partials in index order.  (The one-block-per-
-// feature version with 2-byte loads took 210 us per layer = 48 % of an iteration.)
-constexpr int kRowSplit = 16;
-__global__ void __launch_bounds__(128)
-k_nsf_rowsum(NsfBufs b, const __nv_bfloat16* __restrict__ dT, float* __restrict__ part, int with_w0) {
-  if (b.ctl->stop) return;
-  __shared__ float red[4][4];
-  const int f = blockIdx.x, sp = blockIdx.y;
-  const int nvec = b.n_pad >> 3;
-  const int per = (nvec + kRowSplit - 1) / kRowSplit;
-  const int v0 = sp * per, v1 = min(v0 + per, nvec);
-  const uint4* hi = (const uint4*)(dT + (long long)f * b.n_pad);
-  const uint4* lo = (const uint4*)(dT + b.ps + (long long)f * b.n_pad);
-  float s = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
-  for (int v = v0 + threadIdx.x; v < v1; v += 128) {
-    const uint4 a = hi[v];
-    const uint32_t aa[4] = {a.x, a.y, a.z, a.w};
-    float val[8];
-    if (b.planes == 2) {
-      const uint4 l = lo[v];
-      const uint32_t ll[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&aa[k]));
-        const float2 l2 = __half22float2(*reinterpret_cast<const __half2*>(&ll[k]));
-        val[2 * k] = h2.x + l2.x; val[2 * k + 1] = h2.y + l2.y;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { val[2 * k] = __uint_as_float(aa[k] << 16); val[2 * k + 1] = __uint_as_float(aa[k] & 0xffff0000u); }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      s += val[k];
-      if (with_w0) { const float4 p = b.x4[(size_t)v * 8 + k]; sx = fmaf(val[k], p.x, sx); sy = fmaf(val[k], p.y, sy); sz = fmaf(val[k], p.z, sz); }
-    }
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, d);
-    sx += __shfl_xor_sync(0xffffffffu, sx, d);
-    sy += __shfl_xor_sync(0xffffffffu, sy, d);
-    sz += __shfl_xor_sync(0xffffffffu, sz, d);
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { red[warp][0] = s; red[warp][1] = sx; red[warp][2] = sy; red[warp][3] = sz; }
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    float t = 0.f;
-    for (int wv = 0; wv < 4; ++wv) t += red[wv][threadIdx.x];
-    part[((size_t)sp * 4 + threadIdx.x) * 128 + f] = t;
-  }
+// ------------------------------------------------------------------------------ weight gradients: k_nsf_dw
+// ALL parameter gradients of the hidden layers in ONE launch:
+//   dW_l = delta_{l+1}^T h_l (l = 1..7),  db_l = delta_{l+1}^T 1 (l = 0..7),  dW_0 = delta_1^T x
+// as split-K GEMMs over the points.  CTA c owns the point range [c * k_split, (c+1) * k_split) and walks the eight
+// layers; per layer it accumulates in tensor memory (M = 128 out features of delta_{l+1}, N = 128 in features of h_l,
+// plus a 16-column accumulator against the (x, y, z, 1) tile) and flushes its partial to dW_part / small_part, which
+// k_nsf_small_final / k_nsf_adam add up over the CTAs.  Operands are the ROW-MAJOR tiles of delta and h read as
+// MN-major (see NsfBufs): stage = 32 points: delta tile 4 chunks x 2 planes x 2 KB, h tile the same, x tile 2 x 2 KB.
+// Split fp16 planes -> three MMAs per product (hi*hi, hi*lo, lo*hi) into ONE accumulator (<= 130 MMAs per chain).
+// Accumulators are double-buffered by layer parity so that the flush of layer l overlaps the MMAs of layer l+1.
+// Memory-bound by construction (each stage's 36 KB feed 12 small MMAs): 8 x 100 MB of operands per iteration.
+constexpr int kDwKT = 32;                              // points per stage
+constexpr int kDwChunkB = kDwKT * 64;                  // one 32-feature chunk of one plane: 2 KB
+constexpr int kDwOpB = 4 * 2 * kDwChunkB;              // delta or h tile: 16 KB
+constexpr int kDwStageB = 2 * kDwOpB + 2 * kDwChunkB;  // 36 KB
+constexpr int kDwStages = 5;
+constexpr int kDwBarOffset = kDwStages * kDwStageB;
+constexpr int kDwTotal = kDwBarOffset + 256 + 1024;
+constexpr int kDwThreads = 192;                        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+
+struct DwMaps { CUtensorMap delta[kNsfLayers + 1]; CUtensorMap h[kNsfLayers]; CUtensorMap x; };   // delta[1..8], h[1..7]
+
+__device__ __forceinline__ uint64_t dw_desc_mn(uint32_t addr) {   // MN-major, SWIZZLE_64B: LBO = chunk stride, SBO = 8 rows
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fffu);
+  d |= (uint64_t)(kDwChunkB >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 4ull << 61;
+  return d;
 }
-__global__ void __launch_bounds__(128)
-k_nsf_rowsum_final(NsfBufs b, const float* __restrict__ part, float* __restrict__ out_b, float* __restrict__ out_w0) {
-  if (b.ctl->stop) return;
-  const int f = threadIdx.x;
-  float t[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int sp = 0; sp < kRowSplit; ++sp)
+
+__global__ void __launch_bounds__(kDwThreads, 1)
+k_nsf_dw(const __grid_constant__ DwMaps maps, const int* __restrict__ stop_flag, int n_pad, int k_split, int splits,
+         int planes, float* __restrict__ dW_part, float* __restrict__ small_part) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + kDwBarOffset);
+  uint64_t* empty_bar = full_bar + kDwStages;
+  uint64_t* acc_full = empty_bar + kDwStages;       // [2]
+  uint64_t* acc_empty = acc_full + 2;               // [2]
+  uint32_t* tmem_ptr = (uint32_t*)(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  if (*stop_flag) return;
+  const int cta = blockIdx.x;
+  if (cta >= splits) return;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kDwStages; ++s) { umma::mbar_init(&full_bar[s], 1); umma::mbar_init(&empty_bar[s], 1); }
+    for (int k = 0; k < 2; ++k) { umma::mbar_init(&acc_full[k], 1); umma::mbar_init(&acc_empty[k], 4); }
+    umma::fence_barrier_init();
+  } else if (warp == 1) {
+    umma::tmem_alloc(tmem_ptr, 512);
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int p0 = cta * k_split;
+  const int n_stage = (min(k_split, n_pad - p0) + kDwKT - 1) / kDwKT;
+  // TMEM columns: buffer k: dW accumulator [k*144, +128), small accumulator [k*144 + 128, +16)
+  if (warp == 0) {
+    uint32_t git = 0;
+    for (int l = 0; l < kNsfLayers; ++l) {
+      for (int st = 0; st < n_stage; ++st, ++git) {
+        const int s = git % kDwStages;
+        umma::mbar_wait(&empty_bar[s], ((git / kDwStages) & 1) ^ 1);
+        if (umma::elect_one()) {
+          uint8_t* dst = smem + s * kDwStageB;
+          const int pt = p0 + st * kDwKT;
+          umma::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(planes * (4 * kDwChunkB * (l > 0 ? 2 : 1) + kDwChunkB)));
+          for (int pl = 0; pl < planes; ++pl)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) t[k] += part[((size_t)sp * 4 + k) * 128 + f];
-  out_b[f] = t[0];
-  if (out_w0) { out_w0[f * 3] = t[1]; out_w0[f * 3 + 1] = t[2]; out_w0[f * 3 + 2] = t[3]; }
+            for (int c = 0; c < 4; ++c)
+              umma::tma_load_3d(dst + (pl * 4 + c) * kDwChunkB, &maps.delta[l + 1], &full_bar[s], c * 32, pt, pl);
+          if (l > 0) {
+            for (int pl = 0; pl < planes; ++pl)
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                umma::tma_load_3d(dst + kDwOpB + (pl * 4 + c) * kDwChunkB, &maps.h[l], &full_bar[s], c * 32, pt, pl);
+          }
+          for (int pl = 0; pl < planes; ++pl)
+            umma::tma_load_3d(dst + 2 * kDwOpB + pl * kDwChunkB, &maps.x, &full_bar[s], 0, pt, pl);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t kMN = (1u << 15) | (1u << 16);
+    const uint32_t fmt = planes == 2 ? 0u : 1u;          // split fp16 planes, or one bf16 plane
+    const uint32_t id_big = umma::idesc_f16kind_f32(128, 128, fmt, fmt) | kMN;
+    const uint32_t id_small = umma::idesc_f16kind_f32(128, 16, fmt, fmt) | kMN;
+    const bool split = planes == 2;
+    uint32_t git = 0;
+    for (int l = 0; l < kNsfLayers; ++l) {
+      const int buf = l & 1;
+      umma::mbar_wait(&acc_empty[buf], ((l >> 1) & 1) ^ 1);
+      umma::tc_fence_after();
+      const uint32_t t_big = tmem_base + (uint32_t)(buf * 144), t_small = t_big + 128u;
+      for (int st = 0; st < n_stage; ++st, ++git) {
+        const int s = git % kDwStages;
+        umma::mbar_wait(&full_bar[s], (git / kDwStages) & 1);
+        umma::tc_fence_after();
+        if (umma::elect_one()) {
+          const uint32_t a0 = umma::smem_u32(smem + s * kDwStageB), b0 = a0 + kDwOpB, x0 = a0 + 2 * kDwOpB;
+#pragma unroll
+          for (int k = 0; k < kDwKT / 16; ++k) {
+            const uint32_t ko = (uint32_t)(k * 16 * 64);
+            const uint64_t a_hi = dw_desc_mn(a0 + ko), a_lo = dw_desc_mn(a0 + 4 * kDwChunkB + ko);
+            const uint32_t first = (st == 0 && k == 0) ? 0u : 1u;
+            if (l > 0) {
+              const uint64_t b_hi = dw_desc_mn(b0 + ko), b_lo = dw_desc_mn(b0 + 4 * kDwChunkB + ko);
+              umma::mma_bf16_ss(t_big, a_hi, b_hi, id_big, first);
+              if (split) {
+                umma::mma_bf16_ss(t_big, a_hi, b_lo, id_big, 1u);
+                umma::mma_bf16_ss(t_big, a_lo, b_hi, id_big, 1u);
+              }
+            }
+            const uint64_t x_hi = dw_desc_mn(x0 + ko), x_lo = dw_desc_mn(x0 + kDwChunkB + ko);
+            umma::mma_bf16_ss(t_small, a_hi, x_hi, id_small, first);
+            if (split) {
+              umma::mma_bf16_ss(t_small, a_hi, x_lo, id_small, 1u);
+              umma::mma_bf16_ss(t_small, a_lo, x_hi, id_small, 1u);
+            }
+          }
+          umma::mma_commit(&empty_bar[s]);
+        }
+        __syncwarp();
+      }
+      if (umma::elect_one()) umma::mma_commit(&acc_full[buf]);
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;                 // out feature (row of dW)
+    for (int l = 0; l < kNsfLayers; ++l) {
+      const int buf = l & 1;
+      umma::mbar_wait(&acc_full[buf], (l >> 1) & 1);
+      umma::tc_fence_after();
+      const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 144);
+      if (l > 0) {
+        float* dst = dW_part + ((size_t)(l - 1) * splits + cta) * 16384 + (size_t)m * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          umma::tmem_ld_32x32(t_big + (uint32_t)(c * 32), r);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ((float4*)(dst + c * 32))[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+      }
+      {
+        uint32_t r[16];
+        umma::tmem_ld_32x16(t_big + 128u, r);
+        umma::tmem_ld_wait();
+        *(float4*)(small_part + (((size_t)l * splits + cta) * 128 + m) * 4) =
+            make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+      }
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem_base, 512);
+}
+
+// bias gradients and dW_0 from the split partials of k_nsf_dw: column 3 = delta^T 1, columns 0..2 = delta_1^T x
+__global__ void __launch_bounds__(128)
+k_nsf_small_final(NsfBufs b, int splits) {
+  if (b.ctl->stop) return;
+  const int l = blockIdx.x, m = threadIdx.x;      // layer 0..7, feature
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = *(const float4*)(b.small_part + (((size_t)l * splits + s) * 128 + m) * 4);
+    t[0] += v.x; t[1] += v.y; t[2] += v.z; t[3] += v.w;
+  }
+  if (l == 0) { b.gW0[m * 3] = t[0]; b.gW0[m * 3 + 1] = t[1]; b.gW0[m * 3 + 2] = t[2]; b.gW0[384 + m] = t[3]; }
+  else b.gb[(l - 1) * 128 + m] = t[3];
 }
 
 // ------------------------------------------------------------------------------ generic MLP entry points (NSFP)
@@ -495,95 +627,37 @@ k_nsf_rowsum_final(NsfBufs b, const float* __restrict__ part, float* __restrict_
 __global__ void __launch_bounds__(kHeadThreads)
 k_mlp_head_fwd(NsfBufs b, float* __restrict__ out) {
   if (b.ctl->stop) return;
+  __shared__ float sW8[384];
+  for (int t = threadIdx.x; t < 384; t += kHeadThreads) sW8[t] = b.params[nsf_off_w(8) + t];
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b.n) return;
-  const float* W8 = b.params + nsf_off_w(8);
-  const float* b8 = b.params + nsf_off_b(8);
-  const __nv_bfloat16* hT = b.HT[8];
-  float f0 = 0.f, f1 = 0.f, f2 = 0.f;
-  for (int j = 0; j < 128; ++j) {
-    const float h = load_split(hT + (long long)j * b.n_pad + i, b.ps, b.planes);
-    f0 = fmaf(__ldg(W8 + j), h, f0);
-    f1 = fmaf(__ldg(W8 + 128 + j), h, f1);
-    f2 = fmaf(__ldg(W8 + 256 + j), h, f2);
-  }
-  f0 += __ldg(b8); f1 += __ldg(b8 + 1); f2 += __ldg(b8 + 2);
-  *(float4*)(b.flow + 4 * (size_t)i) = make_float4(f0, f1, f2, 0.f);
-  out[3 * (size_t)i] = f0; out[3 * (size_t)i + 1] = f1; out[3 * (size_t)i + 2] = f2;
+  float f[3];
+  head_flow(b, sW8, i, f);
+  *(float4*)(b.flow + 4 * (size_t)i) = make_float4(f[0], f[1], f[2], 0.f);
+  out[3 * (size_t)i] = f[0]; out[3 * (size_t)i + 1] = f[1]; out[3 * (size_t)i + 2] = f[2];
 }
 
-// backward entry: d_out [n,3] (true scale) -> delta_8 = (d_out W8) * relu'(h8) as row-major and transposed planes,
-// per-block partials of dW8 / db8 in the layout k_nsf_adam reads (same reductions as k_nsf_head: deterministic)
+// backward entry: d_out [n,3] (true scale) -> delta_8 and the dW8 / db8 partials (same reductions as k_nsf_head)
 __global__ void __launch_bounds__(kHeadThreads)
 k_mlp_head_bwd(NsfBufs b, const float* __restrict__ d_out) {
   if (b.ctl->stop) return;
   __shared__ float red[kHeadThreads / 32][4];
   __shared__ float red_w[kHeadThreads / 32][3][128];
-  const float* W8 = b.params + nsf_off_w(8);
+  __shared__ float sW8[384];
+  for (int t = threadIdx.x; t < 384; t += kHeadThreads) sW8[t] = b.params[nsf_off_w(8) + t];
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < b.n;
   const float S = b.grad_scale;
   const float d0 = live ? d_out[3 * (size_t)i] * S : 0.f, d1 = live ? d_out[3 * (size_t)i + 1] * S : 0.f,
               d2 = live ? d_out[3 * (size_t)i + 2] * S : 0.f;
-  const __nv_bfloat16* hT = b.HT[8];
-  float* part = b.head_part + (size_t)blockIdx.x * kHeadPart;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool in_pad = i < b.n_pad;
-  const bool split = b.planes == 2;
-  for (int j0 = 0; j0 < 128; j0 += 8) {
-    uint32_t hi[4], lo[4];
-    float dhv[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u;
-      const float h = in_pad ? load_split(hT + (long long)j * b.n_pad + i, b.ps, b.planes) : 0.f;
-      float dh = fmaf(d2, __ldg(W8 + 256 + j), fmaf(d1, __ldg(W8 + 128 + j), d0 * __ldg(W8 + j)));
-      if (!(h > 0.f)) dh = 0.f;
-      dhv[u] = dh;
-      if (in_pad) umma::store_split(b.DLT[0] + (long long)j * b.n_pad + i, b.ps, b.planes, dh);
-      float a0 = d0 * h, a1 = d1 * h, a2 = d2 * h;
-#pragma unroll
-      for (int sft = 16; sft > 0; sft >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, sft);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
-        a2 += __shfl_xor_sync(0xffffffffu, a2, sft);
-      }
-      if (lane == 0) { red_w[warp][0][j] = a0; red_w[warp][1][j] = a1; red_w[warp][2][j] = a2; }
-    }
-    if (in_pad) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) umma::pack_split2(dhv[2 * u], dhv[2 * u + 1], split, hi[u], lo[u]);
-      *(uint4*)(b.DL[0] + (long long)i * 128 + j0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      if (split) *(uint4*)(b.DL[0] + b.ps + (long long)i * 128 + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < 384; t += kHeadThreads) {
-    const int k = t >> 7, j = t & 127;
-    float sacc = 0.f;
-    for (int wv = 0; wv < kHeadThreads / 32; ++wv) sacc += red_w[wv][k][j];
-    part[k * 128 + j] = sacc;
-  }
-  float a0 = d0, a1 = d1, a2 = d2;
-#pragma unroll
-  for (int sft = 16; sft > 0; sft >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, sft);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, sft);
-  }
-  if (lane == 0) { red[warp][0] = a0; red[warp][1] = a1; red[warp][2] = a2; }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    float t = 0.f;
-    for (int wv = 0; wv < kHeadThreads / 32; ++wv) t += red[wv][threadIdx.x];
-    part[384 + threadIdx.x] = t;
-  }
-  if (threadIdx.x == 3) part[387] = 0.f;
+  head_backward(b, sW8, i, d0, d1, d2, 0.f, red_w, red);
 }
 
-// d loss / d input = delta_1 W0 (the only path from the input: h1 = relu(W0 x + b0)); delta_1 row-major planes
+// d loss / d input = delta_1 W0 (the only path from the input: h1 = relu(W0 x + b0))
 __global__ void __launch_bounds__(128)
-k_mlp_dx(NsfBufs b, const __nv_bfloat16* __restrict__ delta1, float inv_scale, float* __restrict__ dx) {
+k_mlp_dx(NsfBufs b, float inv_scale, float* __restrict__ dx) {
   if (b.ctl->stop) return;
   __shared__ float sW[384];
   for (int t = threadIdx.x; t < 384; t += 128) sW[t] = b.params[nsf_off_w(0) + t];
@@ -592,22 +666,8 @@ k_mlp_dx(NsfBufs b, const __nv_bfloat16* __restrict__ delta1, float inv_scale, f
   if (i >= b.n) return;
   float g0 = 0.f, g1 = 0.f, g2 = 0.f;
   for (int j0 = 0; j0 < 128; j0 += 8) {
-    const uint4 a = *(const uint4*)(delta1 + (long long)i * 128 + j0);
-    const uint32_t aa[4] = {a.x, a.y, a.z, a.w};
     float v[8];
-    if (b.planes == 2) {
-      const uint4 l = *(const uint4*)(delta1 + b.ps + (long long)i * 128 + j0);
-      const uint32_t ll[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&aa[k]));
-        const float2 l2 = __half22float2(*reinterpret_cast<const __half2*>(&ll[k]));
-        v[2 * k] = h2.x + l2.x; v[2 * k + 1] = h2.y + l2.y;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { v[2 * k] = __uint_as_float(aa[k] << 16); v[2 * k + 1] = __uint_as_float(aa[k] & 0xffff0000u); }
-    }
+    load_split8(b.DL[1] + (long long)i * 128 + j0, b.ps, b.planes, v);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int j = j0 + k;
@@ -716,10 +776,26 @@ k_nsf_pack_weights(const float* __restrict__ params, NsfAdamArgs a) {
 }
 
 __global__ void __launch_bounds__(256)
-k_nsf_pack_points(const float* __restrict__ pc, int n, int n_pad, float4* __restrict__ x4) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
-    x4[i] = i < n ? make_float4(pc[3 * (size_t)i], pc[3 * (size_t)i + 1], pc[3 * (size_t)i + 2], 0.f)
-                  : make_float4(0.f, 0.f, 0.f, 0.f);
+k_nsf_pack_points(const float* __restrict__ pc, int n, int n_pad, float4* __restrict__ x4, __nv_bfloat16* __restrict__ x16,
+                  int planes) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+    const bool live = i < n;
+    const float4 p = live ? make_float4(pc[3 * (size_t)i], pc[3 * (size_t)i + 1], pc[3 * (size_t)i + 2], 0.f)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    x4[i] = p;
+    // (x, y, z, 1, 0 x 28) as split planes: the B operand of k_nsf_dw's 16-column accumulator (dW_0 and every bias gradient)
+    uint32_t hi[2], lo[2];
+    umma::pack_split2(p.x, p.y, planes == 2, hi[0], lo[0]);
+    umma::pack_split2(p.z, live ? 1.f : 0.f, planes == 2, hi[1], lo[1]);
+    uint4* d0 = (uint4*)(x16 + (size_t)i * 32);
+    d0[0] = make_uint4(hi[0], hi[1], 0u, 0u); d0[1] = make_uint4(0u, 0u, 0u, 0u);
+    d0[2] = make_uint4(0u, 0u, 0u, 0u); d0[3] = make_uint4(0u, 0u, 0u, 0u);
+    if (planes == 2) {
+      uint4* d1 = (uint4*)(x16 + (size_t)n_pad * 32 + (size_t)i * 32);
+      d1[0] = make_uint4(lo[0], lo[1], 0u, 0u); d1[1] = make_uint4(0u, 0u, 0u, 0u);
+      d1[2] = make_uint4(0u, 0u, 0u, 0u); d1[3] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -744,9 +820,9 @@ static size_t nsf_layout(int n_max, int planes, NsfLayout* L, void* base) {
   const size_t act = (size_t)planes * n_pad * 128;
   NsfLayout l;
   l.b.x4 = A.take<float4>(n_pad);
-  for (int k = 1; k <= kNsfLayers; ++k) { l.b.H[k] = A.take<__nv_bfloat16>(act); l.b.HT[k] = A.take<__nv_bfloat16>(act); }
-  l.b.H[0] = l.b.HT[0] = nullptr;
-  for (int k = 0; k < 2; ++k) { l.b.DL[k] = A.take<__nv_bfloat16>(act); l.b.DLT[k] = A.take<__nv_bfloat16>(act); }
+  l.b.x16 = A.take<__nv_bfloat16>((size_t)planes * n_pad * 32);
+  for (int k = 1; k <= kNsfLayers; ++k) { l.b.H[k] = A.take<__nv_bfloat16>(act); l.b.DL[k] = A.take<__nv_bfloat16>(act); }
+  l.b.H[0] = l.b.DL[0] = nullptr;
   l.b.params = A.take<float>(kNsfParams);
   l.ad.m = A.take<float>(kNsfParams);
   l.ad.v = A.take<float>(kNsfParams);
@@ -756,11 +832,11 @@ static size_t nsf_layout(int n_max, int planes, NsfLayout* L, void* base) {
   l.b.head_part = A.take<float>((size_t)l.head_blocks * kHeadPart);
   l.b.gW0 = A.take<float>(128 * 3 + 128);
   l.b.gb = A.take<float>(7 * 128);
-  l.b.rs_part = A.take<float>(16 * 4 * 128);
   l.b.ctl = A.take<NsfCtl>(1);
   l.k_split = 32 * ceil_div(n_pad, 32 * kNumSMs);
   l.splits = ceil_div(n_pad, l.k_split);
   l.dW_part = A.take<float>((size_t)7 * l.splits * 16384);
+  l.b.small_part = A.take<float>((size_t)8 * l.splits * 128 * 4);
   for (int k = 1; k < kNsfLayers; ++k) {
     l.ad.Wp[k] = A.take<__nv_bfloat16>((size_t)planes * 16384);
     l.ad.WpT[k] = A.take<__nv_bfloat16>((size_t)planes * 16384);
@@ -786,42 +862,67 @@ static int nsf_forward_hidden(const NsfBufs& b, const NsfAdamArgs& ad, cudaStrea
     g.in = b.H[l]; g.in_planes = P; g.in_plane_stride = b.ps; g.H_in = n_pad / 128; g.W_in = 128;
     g.Cin_total = 128; g.Cin = 128; g.wgt = ad.Wp[l]; g.bias = b.params + nsf_off_b(l); g.Cout = 128; g.ksize = 1;
     g.stride = 1; g.out = b.H[l + 1]; g.out_planes = P; g.out_plane_stride = b.ps; g.Cout_total = 128; g.act = 4;
-    g.n_groups = 1; g.acc_scale = wscale; g.out_t = b.HT[l + 1]; g.out_t_plane_stride = b.ps; g.ld_t = n_pad;
-    g.stop_flag = &b.ctl->stop;
+    g.n_groups = 1; g.acc_scale = wscale; g.stop_flag = &b.ctl->stop;
     HIMO_RET(nsf_gemm(g, stream));
   }
   return HIMO_OK;
 }
 
-// From delta_8 in DL[0] / DLT[0]: for l = 7..1  dW_l = delta_{l+1}^T h_l (split-K over the points), db_l = row sums,
-// delta_l = (delta_{l+1} W_l) * relu'(h_l); then dW_0, db_0 from delta_1.  *cur_out: which DL / DLT pair holds delta_1.
+static PFN_cuTensorMapEncodeTiled nsf_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled)p;
+  }
+  return fn;
+}
+// [planes][n_pad][C] 16-bit tensor, box = (32 features, kDwKT points, 1 plane), 64-byte swizzle
+static int nsf_map_rows(CUtensorMap* m, const void* base, int planes, int n_pad, int C) {
+  PFN_cuTensorMapEncodeTiled enc = nsf_encode_fn();
+  if (!enc) return HIMO_ERR_UNSUPPORTED;
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)n_pad, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)n_pad * C * 2};
+  cuuint32_t box[3] = {32, (cuuint32_t)kDwKT, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? HIMO_OK : HIMO_ERR_ARG;
+}
+
+// From delta_8 in DL[8]: delta_l = (delta_{l+1} W_l) * relu'(h_l) for l = 7..1 (GEMMs with the ReLU mask in the epilogue),
+// then every weight / bias gradient of layers 0..7 in one launch (k_nsf_dw) and the small reductions.
 static int nsf_backward_hidden(const NsfBufs& b, const NsfAdamArgs& ad, float* dW_part, int splits, int k_split,
-                               int* cur_out, cudaStream_t stream) {
+                               cudaStream_t stream) {
   const int P = b.planes, n_pad = b.n_pad;
   const float wscale = P == 2 ? 1.0f / kNsfWScale : 1.0f;
-  int cur = 0;
   for (int l = kNsfLayers - 1; l >= 1; --l) {
-    himo_conv_desc g = {};
-    g.in = b.DLT[cur]; g.in_planes = P; g.in_plane_stride = b.ps; g.H_in = 1; g.W_in = 128;
-    g.Cin_total = n_pad; g.Cin = k_split; g.wgt = b.HT[l]; g.bias = nullptr; g.Cout = 128; g.ksize = 1; g.stride = 1;
-    g.out = dW_part + (size_t)(l - 1) * splits * 16384; g.out_fp32 = 1; g.out_planes = 1; g.Cout_total = 128;
-    g.n_groups = splits; g.cin_group_stride = k_split; g.cout_group_stride = 0; g.acc_scale = 1.f;
-    g.b_group_k_stride = k_split; g.out_group_pix_stride = 128; g.b_k_total = n_pad; g.stop_flag = &b.ctl->stop;
-    HIMO_RET(nsf_gemm(g, stream));
-    k_nsf_rowsum<<<dim3(128, kRowSplit), 128, 0, stream>>>(b, b.DLT[cur], b.rs_part, 0); HIMO_LAUNCH_RET();
-    k_nsf_rowsum_final<<<1, 128, 0, stream>>>(b, b.rs_part, b.gb + (l - 1) * 128, nullptr); HIMO_LAUNCH_RET();
     himo_conv_desc q = {};
-    q.in = b.DL[cur]; q.in_planes = P; q.in_plane_stride = b.ps; q.H_in = n_pad / 128; q.W_in = 128;
+    q.in = b.DL[l + 1]; q.in_planes = P; q.in_plane_stride = b.ps; q.H_in = n_pad / 128; q.W_in = 128;
     q.Cin_total = 128; q.Cin = 128; q.wgt = ad.WpT[l]; q.bias = nullptr; q.Cout = 128; q.ksize = 1; q.stride = 1;
-    q.out = b.DL[cur ^ 1]; q.out_planes = P; q.out_plane_stride = b.ps; q.Cout_total = 128; q.act = 0;
-    q.n_groups = 1; q.acc_scale = wscale; q.out_t = b.DLT[cur ^ 1]; q.out_t_plane_stride = b.ps; q.ld_t = n_pad;
+    q.out = b.DL[l]; q.out_planes = P; q.out_plane_stride = b.ps; q.Cout_total = 128; q.act = 0;
+    q.n_groups = 1; q.acc_scale = wscale;
     q.mask_src = b.H[l]; q.mask_plane_stride = b.ps; q.mask_planes = P; q.stop_flag = &b.ctl->stop;
     HIMO_RET(nsf_gemm(q, stream));
-    cur ^= 1;
   }
-  k_nsf_rowsum<<<dim3(128, kRowSplit), 128, 0, stream>>>(b, b.DLT[cur], b.rs_part, 1); HIMO_LAUNCH_RET();
-  k_nsf_rowsum_final<<<1, 128, 0, stream>>>(b, b.rs_part, b.gW0 + 384, b.gW0); HIMO_LAUNCH_RET();
-  if (cur_out) *cur_out = cur;
+  DwMaps maps;
+  for (int l = 1; l <= kNsfLayers; ++l) HIMO_RET(nsf_map_rows(&maps.delta[l], b.DL[l], P, n_pad, 128));
+  maps.delta[0] = maps.delta[1];
+  for (int l = 1; l < kNsfLayers; ++l) HIMO_RET(nsf_map_rows(&maps.h[l], b.H[l], P, n_pad, 128));
+  maps.h[0] = maps.h[1];
+  HIMO_RET(nsf_map_rows(&maps.x, b.x16, P, n_pad, 32));
+  static bool configured_dev[64] = {};
+  int dev_ = 0;
+  HIMO_CUDA_RET(cudaGetDevice(&dev_));
+  if (!configured_dev[dev_ & 63]) {
+    HIMO_CUDA_RET(cudaFuncSetAttribute(k_nsf_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwTotal));
+    configured_dev[dev_ & 63] = true;
+  }
+  k_nsf_dw<<<splits, kDwThreads, kDwTotal, stream>>>(maps, &b.ctl->stop, n_pad, k_split, splits, P, dW_part, b.small_part);
+  HIMO_LAUNCH_RET();
+  k_nsf_small_final<<<kNsfLayers, 128, 0, stream>>>(b, splits); HIMO_LAUNCH_RET();
   return HIMO_OK;
 }
 
@@ -938,7 +1039,7 @@ extern "C" int himo_nsf_optimize(const himo_nsf_desc* d, void* stream_) {
   c0.best_loss = INFINITY;
   HIMO_CUDA_RET(cudaMemcpyAsync(b.ctl, &c0, sizeof(NsfCtl), cudaMemcpyHostToDevice, stream));
   HIMO_CUDA_RET(cudaMemsetAsync(b.best_flow, 0, sizeof(float) * 4 * n_pad, stream));
-  k_nsf_pack_points<<<min(ceil_div(n_pad, 256), kNumSMs * 8), 256, 0, stream>>>(d->pc0, n, n_pad, (float4*)b.x4);
+  k_nsf_pack_points<<<min(ceil_div(n_pad, 256), kNumSMs * 8), 256, 0, stream>>>(d->pc0, n, n_pad, (float4*)b.x4, b.x16, P);
   HIMO_LAUNCH_RET();
   k_nsf_pack_weights<<<kNumSMs * 2, 256, 0, stream>>>(b.params, ad);
   HIMO_LAUNCH_RET();
@@ -948,8 +1049,7 @@ extern "C" int himo_nsf_optimize(const himo_nsf_desc* d, void* stream_) {
     k_nsf_head<<<head_blocks, kHeadThreads, 0, stream>>>(b, d->D, vol); HIMO_LAUNCH_RET();
     k_nsf_control<<<1, 32, 0, stream>>>(b, head_blocks, d->min_delta, d->patience); HIMO_LAUNCH_RET();
     k_nsf_snapshot<<<min(ceil_div(n, 256), kNumSMs * 4), 256, 0, stream>>>(b); HIMO_LAUNCH_RET();
-    int cur = 0;
-    HIMO_RET(nsf_backward_hidden(b, ad, L.dW_part, splits, k_split, &cur, stream));
+    HIMO_RET(nsf_backward_hidden(b, ad, L.dW_part, splits, k_split, stream));
     k_nsf_adam<<<kNumSMs * 2, 256, 0, stream>>>(ad); HIMO_LAUNCH_RET();
     return HIMO_OK;
   };
@@ -1014,7 +1114,8 @@ extern "C" int himo_mlp_forward(void* workspace, size_t workspace_bytes, int n_m
   if (!x || !out) return HIMO_ERR_ARG;
   HIMO_RET(nsf_call_setup(workspace, workspace_bytes, n_max, planes, n, 0.f, &c));
   c.b.ctl = mlp_ctl(ctl_workspace, n_max, planes, c.b.ctl);
-  k_nsf_pack_points<<<min(ceil_div(c.b.n_pad, 256), kNumSMs * 8), 256, 0, stream>>>(x, n, c.b.n_pad, (float4*)c.b.x4);
+  k_nsf_pack_points<<<min(ceil_div(c.b.n_pad, 256), kNumSMs * 8), 256, 0, stream>>>(x, n, c.b.n_pad, (float4*)c.b.x4,
+                                                                                    c.b.x16, planes);
   HIMO_LAUNCH_RET();
   HIMO_RET(nsf_forward_hidden(c.b, c.ad, stream));
   k_mlp_head_fwd<<<c.head_blocks, kHeadThreads, 0, stream>>>(c.b, out); HIMO_LAUNCH_RET();
@@ -1029,10 +1130,9 @@ extern "C" int himo_mlp_backward(void* workspace, size_t workspace_bytes, int n_
   HIMO_RET(nsf_call_setup(workspace, workspace_bytes, n_max, planes, n, 0.f, &c));
   c.b.ctl = mlp_ctl(ctl_workspace, n_max, planes, c.b.ctl);
   k_mlp_head_bwd<<<c.head_blocks, kHeadThreads, 0, stream>>>(c.b, d_out); HIMO_LAUNCH_RET();
-  int cur = 0;
-  HIMO_RET(nsf_backward_hidden(c.b, c.ad, c.L.dW_part, c.splits, c.k_split, &cur, stream));
+  HIMO_RET(nsf_backward_hidden(c.b, c.ad, c.L.dW_part, c.splits, c.k_split, stream));
   if (d_x) {
-    k_mlp_dx<<<ceil_div(n, 128), 128, 0, stream>>>(c.b, c.b.DL[cur], c.ad.inv_scale, d_x);
+    k_mlp_dx<<<ceil_div(n, 128), 128, 0, stream>>>(c.b, c.ad.inv_scale, d_x);
     HIMO_LAUNCH_RET();
   }
   return HIMO_OK;

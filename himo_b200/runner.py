@@ -271,7 +271,10 @@ def run_eval(cfg: Dict[str, str]):
     zip_path = cfg.get("comp_dis_zip", "")
     data_name, flag = himo.check_valid(data_dir, res_name, zip_path)
     rank, world, local = _dist_env()
-    metrics = himo.InstanceMetrics(data_name)
+    # the per-instance Chamfer of every frame runs as one batched device launch when a GPU is there (himo_segmented_nn);
+    # `metrics_device=host` forces the reference's scipy path
+    mdev = cfg.get("metrics_device", f"cuda:{local}" if torch.cuda.is_available() and local < torch.cuda.device_count() else "host")
+    metrics = himo.InstanceMetrics(data_name, device=None if mdev == "host" else mdev)
     ds = HDF5Dataset(data_dir, vis_name=res_name if flag == 2 else "", eval=True)
     for i in range(rank, len(ds), world):
         data = ds[i]

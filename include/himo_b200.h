@@ -106,6 +106,18 @@ int himo_chamfer_backward(const float* pc0, int n0, const float* pc1, int n1, co
 int himo_chamfer_set_warp_search(int enable);
 
 /* ------------------------------------------------------------------------------------------
+ * (f)3  batched per-instance bidirectional nearest-neighbour distances (instance-level Chamfer of the HiMo metric)
+ * replaces: the per-instance scipy cKDTree queries of `cal_chamfer` (eval.py:50-62) inside InstanceMetrics.step_eval
+ *           (eval.py:88-96) and of tools/test/score.py:262-275, for ALL instances of a frame in one launch.
+ * a, b        [na,3], [nb,3] float64 DEVICE: the points of every instance, instance by instance
+ * a_off,b_off [n_seg+1] int32 DEVICE: CSR offsets of the instances in a / b
+ * dist_a[i]   = min_j |a_i - b_j| over the points b_j of the SAME instance (dist_b likewise); +inf if it has none
+ * max_seg_points = the largest instance size in a or b (sizes the grid).  Exact (brute force), float64 like the reference.
+ */
+int himo_segmented_nn(const double* a, const int32_t* a_off, const double* b, const int32_t* b_off, int n_seg,
+                      int max_seg_points, double* dist_a, double* dist_b, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * H4  dense convolution of the SeFlow++ backbone (tcgen05 implicit GEMM) and 2x bilinear upsample
  * replaces: the ATen/cuDNN work behind nn.Conv2d (+ BatchNorm2d + GELU) in
  *           ConvWithNorms.forward (OSF/src/models/basic/__init__.py:76-94) and

@@ -127,3 +127,34 @@ def test_nnd_autolabel_matches_bruteforce(tmp_path):
             assert got.dtype == np.uint8 and (got == ref).all()
             moving += int(ref.sum())
     assert moving > 0
+
+
+def test_instance_chamfer_on_device_equals_host_path(data_dir):
+    """(f)3: InstanceMetrics with the batched device Chamfer (himo_segmented_nn) against the reference's scipy path
+    (eval.py:50-62) -- per-instance values to 1e-9, the whole eval.py result table equal."""
+    rng = np.random.default_rng(3)
+    pairs = [(rng.normal(size=(n, 3)) * 2 + k, rng.normal(size=(m, 3)) * 2 + k)
+             for k, (n, m) in enumerate([(10, 10), (1, 7), (300, 257), (4000, 3500), (513, 12)])]
+    got = himo.chamfer_mean_nn_batched(pairs, "cuda")
+    ref = [himo.chamfer_mean_nn(a, b) for a, b in pairs]
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9)
+    from himo_b200 import runner
+    j_host, j_dev = os.path.join(data_dir, "m_host.json"), os.path.join(data_dir, "m_dev.json")
+    store.write_synthetic_dataset  # (the module fixture already holds a scored dataset with a stored flow)
+    _run(["save.py", "checkpoint=synthetic:4", f"dataset_path={data_dir}", "res_name=seflowpp_synth"])
+    runner.run_eval({"data_dir": data_dir, "res_name": "seflowpp_synth", "out_json": j_host, "metrics_device": "host"})
+    runner.run_eval({"data_dir": data_dir, "res_name": "seflowpp_synth", "out_json": j_dev, "metrics_device": "cuda:0"})
+    a, b = json.load(open(j_host)), json.load(open(j_dev))
+
+    def walk(x, y):
+        assert type(x) is type(y)
+        if isinstance(x, dict):
+            assert x.keys() == y.keys()
+            for k in x:
+                walk(x[k], y[k])
+        elif isinstance(x, float):
+            assert abs(x - y) <= 1e-9 * max(1.0, abs(x)), (x, y)
+        else:
+            assert x == y
+    walk(a, b)
+    assert len(a["av2"]["seflowpp_synth"]) > 0
