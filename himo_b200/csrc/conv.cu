@@ -114,7 +114,11 @@ __device__ __forceinline__ float gelu_erf(float v) {
 // channels per plane -- is loaded into shared memory ONCE per CTA and every pipeline stage carries only the
 // activation tile.  For the 64-channel encoder layers the weights (74 / 147 KB) were re-fetched from L2 for every
 // 128-pixel tile and out-weighed the activation traffic 3:2.
-template <int BN, int P, int NX, int CG, int WR = 0>
+// TS ("TMA store"): the epilogue streams TMEM -> bias / activation -> a 128-byte-swizzled staging tile in shared memory
+// (64 channels x 128 pixels x both planes = 32 KB) and ONE thread hands it to TMA, instead of every thread storing
+// 16-byte pieces 2*Cout_total bytes apart (32 half-filled sectors per warp store: the tile trace showed ~10 k cycles of
+// stores per 128x128 tile, profiles/r02_conv_tile_trace_enc2_after.txt).  Requires a single accumulation chunk per tile.
+template <int BN, int P, int NX, int CG, int WR = 0, int TS = 0>
 struct ConvCfg {
   static constexpr int kARows = NX == 3 ? 136 : 128;                 // smem rows reserved per A plane
   static constexpr int kARowsTx = NX == 3 ? 130 : 128;               // rows TMA really writes
@@ -124,14 +128,18 @@ struct ConvCfg {
   static constexpr int kBResBytes = WR * P * kBBytes;
   static constexpr int kStageBytes = WR ? P * kABytes : P * kABytes + NX * P * kBBytes;
   static constexpr int kTxBytes = WR ? P * kARowsTx * kConvRowB : P * kARowsTx * kConvRowB + NX * P * kBBytes;
-  static constexpr int kStagesRaw = (220 * 1024 - kBResBytes) / kStageBytes;
+  static constexpr int kOutStageBytes = TS ? 2 * 2 * 128 * 128 : 0; // two [plane][128 px][64 ch] staging tiles of the TMA-store epilogue
+  static constexpr int kStagesRaw = (219 * 1024 - kBResBytes - kOutStageBytes) / kStageBytes;
   static constexpr int STAGES = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kBResOffset = STAGES * kStageBytes;          // (TMA and tcgen05 both swizzle on absolute address bits)
-  static constexpr int kBarOffset = kBResOffset + kBResBytes;
+  static constexpr int kOutOffset = (kBResOffset + kBResBytes + 1023) / 1024 * 1024;   // 1024-aligned (SWIZZLE_128B) from a 1024-aligned base
+  static constexpr int kBarOffset = TS ? kOutOffset + kOutStageBytes : kBResOffset + kBResBytes;
   static_assert(WR == 0 || CG == 1, "resident weights are implemented for single-CTA tiles");
   static constexpr int kBiasOffset = kBarOffset + 512;               // fp32 bias vector staged once per CTA
   static constexpr int kMaxBias = 1024;
-  static constexpr int kTotal = kBiasOffset + kMaxBias * 4 + 128;   // barriers + bias + alignment slack
+  static constexpr int kAlign = TS ? 1024 : 128;
+  static constexpr int kTotal = kBiasOffset + kMaxBias * 4 + kAlign;   // barriers + bias + alignment slack
+  static_assert(!TS || (P == 2 && BN % 64 == 0 && WR == 0), "TMA-store epilogue: split planes, 64-channel chunks");
   // split mode: 2 main + 1 or 2 cross accumulators, then 8 staging slots x 16 columns for the A slices in TMEM
   static constexpr int kCrossBufs = (P == 2 && 4 * BN <= 512) ? 2 : 1;
   static constexpr int kAccCols = P == 2 ? (2 + kCrossBufs) * BN : 2 * BN;
@@ -377,18 +385,18 @@ __device__ __forceinline__ void conv_epilogue_fast(const float* acc, const ConvP
 // tiles -- 6 stages for the 64-channel layers, 4 for the FastNSF GEMMs -- that bubble was ~20 % of a tile).
 // The kernel is persistent: one CTA per SM walks the tile list, barrier phases run across tiles, and the
 // store epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int P, int NX, int CG, int WR = 0>
+template <int BN, int P, int NX, int CG, int WR = 0, int TS = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const ConvParams p) {
-  using C = ConvCfg<BN, P, NX, CG, WR>;
+            const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
+  using C = ConvCfg<BN, P, NX, CG, WR, TS>;
   constexpr int STAGES = C::STAGES;
   constexpr int kHalf = BN / 2;            // columns owned by one epilogue thread
   constexpr int kGroups = kHalf / 16;
   static_assert(kHalf % 16 == 0, "BN must be a multiple of 32");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + (C::kAlign - 1)) & ~(uintptr_t)(C::kAlign - 1));
   uint64_t* full_bar = (uint64_t*)(smem + C::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full_bar = empty_bar + STAGES;     // [2]
@@ -415,6 +423,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     umma::tma_prefetch_desc(&tmA);
     umma::tma_prefetch_desc(&tmB);
+    if (TS) umma::tma_prefetch_desc(&tmO);
     for (int s = 0; s < STAGES; ++s) {
       umma::mbar_init(&full_bar[s], 1);
       umma::mbar_init(&empty_bar[s], 1);
@@ -601,6 +610,100 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ===================== epilogue (8 warps: 2 per TMEM lane quadrant) =====================
+    if constexpr (TS) {
+      // ---- streaming epilogue with TMA stores (one accumulation chunk per tile, see ConvCfg)
+      const int q = warp & 3, hh = (warp - 2) >> 2, row = q * 32 + lane;
+      const bool issuer = warp == 2 && lane == 0;
+      uint8_t* stg0 = smem + C::kOutOffset;
+      const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+      const uint32_t ae0 = CG == 2 ? umma::mapa_u32(umma::smem_u32(&acc_empty_bar[0]), 0) : 0u;
+      const uint32_t ae1 = CG == 2 ? umma::mapa_u32(umma::smem_u32(&acc_empty_bar[1]), 0) : 0u;
+      const uint32_t ce0 = CG == 2 ? umma::mapa_u32(umma::smem_u32(&cross_empty_bar[0]), 0) : 0u;
+      const uint32_t ce1 = CG == 2 ? umma::mapa_u32(umma::smem_u32(&cross_empty_bar[1]), 0) : 0u;
+      uint32_t gch = 0, tcount = 0, npass = 0;
+      for (int tile = worker; tile < total_work; tile += n_workers, ++tcount, ++gch) {
+        int g, x0, y0, n0;
+        decode(tile, g, x0, y0, n0);
+        const int buf = gch & 1;
+        const uint32_t xb = C::kCrossBufs == 2 ? (tcount & 1) : 0u;
+        umma::mbar_wait(&acc_full_bar[buf], (gch >> 1) & 1);
+        umma::tc_fence_after();
+        const uint32_t t_main = tmem_base + lane_base + (uint32_t)(buf * BN);
+        const uint32_t t_cross = tmem_base + lane_base + (uint32_t)((2 + xb) * BN);
+        const int py = y0 + row / p.TW, px = x0 + row % p.TW;
+        const long long pix = (long long)py * p.W_out + px;
+        const int ch_tile = p.cout_off + g * p.cout_group_stride + n0;
+#pragma unroll 1
+        for (int pass = 0; pass < BN / 64; ++pass, ++npass) {
+          uint8_t* stg = stg0 + (npass & 1u) * 32768u;          // two staging tiles: a store stays in flight while the next is filled
+          if (issuer) umma::tma_store_wait_read_but1();         // the store issued two passes ago has read this tile
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+          for (int g2 = 0; g2 < 2; ++g2) {
+            const int col = pass * 64 + hh * 32 + g2 * 16;      // column of the BN-wide tile
+            uint32_t m[16], c[16];
+            umma::tmem_ld_32x16(t_main + (uint32_t)col, m);
+            umma::tmem_ld_32x16(t_cross + (uint32_t)col, c);
+            umma::tmem_ld_wait();
+            float v[16];
+            const float* bs = bias_smem + n0 + col;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x = __fmaf_rn(__uint_as_float(m[j]) + __uint_as_float(c[j]), p.acc_scale, bs[j]);
+              if (p.act == 1) v[j] = gelu_erf(x);
+              else if (p.act == 4) v[j] = fmaxf(x, 0.f);
+              else if (p.act == 2) v[j] = fast_sigmoid(x);
+              else if (p.act == 3) v[j] = fast_tanh(x);
+              else v[j] = x;
+            }
+            if (p.mask_src) {   // ReLU backward: pass the gradient where the forward activation was > 0
+              const __nv_bfloat16* mk = p.mask_src + pix * p.Cout_total + ch_tile + col;
+              uint32_t mb[8];
+              *(uint4*)&mb[0] = *(const uint4*)mk;
+              *(uint4*)&mb[4] = *(const uint4*)(mk + 8);
+              if (p.mask_planes == 2) {
+                uint32_t m2[8];
+                *(uint4*)&m2[0] = *(const uint4*)(mk + p.mask_plane_stride);
+                *(uint4*)&m2[4] = *(const uint4*)(mk + p.mask_plane_stride + 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mb[j] |= m2[j];
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if ((mb[j] & 0x00007fffu) == 0u) v[2 * j] = 0.f;
+                if ((mb[j] & 0x7fff0000u) == 0u) v[2 * j + 1] = 0.f;
+              }
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) umma::pack_split2(v[2 * j], v[2 * j + 1], true, hi[j], lo[j]);
+            // staging tile: [plane][128 rows][128 B], 16-byte unit u of row r lives at u ^ (r & 7)  (SWIZZLE_128B)
+            const int u0 = hh * 4 + g2 * 2;
+            uint8_t* r0 = stg + row * 128;
+            *(uint4*)(r0 + (((u0) ^ (row & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *(uint4*)(r0 + (((u0 + 1) ^ (row & 7)) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            *(uint4*)(r0 + 16384 + (((u0) ^ (row & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *(uint4*)(r0 + 16384 + (((u0 + 1) ^ (row & 7)) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          }
+          if (pass == BN / 64 - 1) {      // the accumulators of this tile have been read: the MMA warp may reuse them
+            umma::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) { umma::mbar_arrive_cluster(buf ? ae1 : ae0); umma::mbar_arrive_cluster(xb ? ce1 : ce0); }
+              else { umma::mbar_arrive(&acc_empty_bar[buf]); umma::mbar_arrive(&cross_empty_bar[xb]); }
+            }
+          }
+          umma::fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (issuer) {
+            umma::tma_store_4d(&tmO, stg, ch_tile + pass * 64, x0, y0, 0);
+            umma::tma_store_4d(&tmO, stg + 16384, ch_tile + pass * 64, x0, y0, 1);
+            umma::tma_store_commit();
+          }
+        }
+      }
+      if (issuer) umma::tma_store_wait_all();
+    } else {
     const int q = warp & 3;                           // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;                 // which half of the BN columns
     const int row = q * 32 + lane;                    // tile row = output pixel within the tile
@@ -682,6 +785,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         default: conv_epilogue<6, kHalf>(acc, p, pix, ch0, bias); break;
       }
     }
+    }   // !TS
   }
   umma::tc_fence_before();
   __syncthreads();
@@ -1154,14 +1258,21 @@ static int g_weights_resident = 1;
 static int g_wide_tiles = 1;
 static int g_pair_min_mmas = 48;
 static int g_max_sms = kNumSMs;   // experiment knob: SMs a persistent launch may occupy
+// Streaming epilogue with TMA stores for short-K 128-wide tiles (ConvCfg TS).  Correct (tests/test_gpu_conv.py runs it), but
+// measured SLOWER than the per-thread stores on the one shape it targets -- the FastNSF 128x128 GEMM: 34.3 -> 47.1 us with
+// double-buffered staging tiles (profiles/r02_conv_tma_store_ab.txt).  Those GEMMs turned out to be bound by SM<->L2 bytes
+// (128 KB of operands + 64 KB of output per 128-point tile at ~30 B/cycle/SM), not by the store instruction pattern, and the
+// staging adds two block-wide barriers per 64 columns.  Off by default; kept as an A/B knob.
+static int g_tma_store = 0;
 static long long* g_dbg = nullptr;
 static int g_rows2 = 1;    // two output rows per CTA pair for the 96-channel decoder-half layers (k_conv_rows2)
 static int g_pdl = 1;      // programmatic dependent launch between the backbone's kernels
 
-template <int BN, int P, int NX, int CG, int WR = 0>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
-  using C = ConvCfg<BN, P, NX, CG, WR>;
-  auto kern = k_conv_umma<BN, P, NX, CG, WR>;
+template <int BN, int P, int NX, int CG, int WR = 0, int TS = 0>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream,
+                       const CUtensorMap* tmO = nullptr) {
+  using C = ConvCfg<BN, P, NX, CG, WR, TS>;
+  auto kern = k_conv_umma<BN, P, NX, CG, WR, TS>;
   static bool configured_dev[64] = {};      // the attribute is per device: one flag per device ordinal
   int dev_ = 0;
   HIMO_CUDA_RET(cudaGetDevice(&dev_));
@@ -1181,7 +1292,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
-  HIMO_CUDA_RET(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  HIMO_CUDA_RET(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO ? *tmO : tmA, p));
   HIMO_LAUNCH_RET();
   return HIMO_OK;
 }
@@ -1209,6 +1320,8 @@ extern "C" int himo_conv_set_pair_min_mmas(int n) { g_pair_min_mmas = n; return 
 extern "C" int himo_conv_set_wide_tiles(int enable) { g_wide_tiles = enable ? 1 : 0; return HIMO_OK; }
 // A/B knob: 0 disables the weights-resident variants of the 64-channel encoder layers.
 extern "C" int himo_conv_set_weights_resident(int enable) { g_weights_resident = enable ? 1 : 0; return HIMO_OK; }
+// A/B knob: 0 disables the TMA-store epilogue (every thread stores its own 16-byte pieces).
+extern "C" int himo_conv_set_tma_store(int enable) { g_tma_store = enable ? 1 : 0; return HIMO_OK; }
 // Profiling hook: device buffer of [grid][32][8] int64 that k_conv_umma fills with clock64() marks per tile (NULL = off).
 extern "C" int himo_conv_set_debug_buffer(void* buf) { g_dbg = (long long*)buf; return HIMO_OK; }
 // A/B knob: 0 disables the two-output-rows tiles (k_conv_rows2) of the 96-channel decoder-half layers.
@@ -1385,6 +1498,27 @@ extern "C" int himo_conv2d_nhwc(const himo_conv_desc* d, void* stream_) {
   if (g_weights_resident && BN == 64 && P == 2 && CGsel == 1 && d->Cout == 64 && d->b_group_k_stride == 0 && !d->b_k_total) {
     if (halo && taps * p.k_chunks == 18) return launch_conv<64, 2, 3, 1, 18>(tmA, tmB, p, stream);
     if (!halo && taps * p.k_chunks == 9) return launch_conv<64, 2, 1, 1, 9>(tmA, tmB, p, stream);
+  }
+  // streaming epilogue + TMA stores: split-plane 128-wide tiles whose whole K fits one accumulation chain (<= 96 hi*hi MMAs)
+  {
+    const int per_stage = 2 * (halo ? 3 : 1);
+    const int k_iters = (taps / (halo ? 3 : 1)) * p.k_chunks;
+    if (g_tma_store && !halo && P == 2 && BN == 128 && d->act < 5 && !d->out_fp32 && d->out_planes == 2 && !d->out_t &&
+        !d->border_bias && d->out_group_pix_stride == 0 && !d->b_k_total && d->b_group_k_stride == 0 &&
+        k_iters * per_stage <= 96 && d->Cout <= 1024 && d->cout_off % 8 == 0) {
+      CUtensorMap tmO;
+      cuuint64_t dimso[4] = {(cuuint64_t)d->Cout_total, (cuuint64_t)W_out, (cuuint64_t)H_out, 2};
+      cuuint64_t strideso[3] = {(cuuint64_t)d->Cout_total * 2, (cuuint64_t)W_out * d->Cout_total * 2,
+                                (cuuint64_t)d->out_plane_stride * 2};
+      cuuint32_t boxo[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+      cuuint32_t estro[4] = {1, 1, 1, 1};
+      if (enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, dimso, strideso, boxo, estro, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return HIMO_ERR_ARG;
+      p.flush_stages = k_iters;                  // one chain: the streaming epilogue reads the accumulators once
+      if (CGsel == 2) return launch_conv<128, 2, 1, 2, 0, 1>(tmA, tmB, p, stream, &tmO);
+      return launch_conv<128, 2, 1, 1, 0, 1>(tmA, tmB, p, stream, &tmO);
+    }
   }
 #define HIMO_CONV_CASE(bn, pp)                                                                        \
   if (BN == bn && P == pp) {                                                                          \

@@ -190,6 +190,10 @@ int himo_conv_set_wide_tiles(int enable);
 /* A/B knob: 0 disables the weights-resident variants (whole weight tensor in shared memory) of the 64-channel
  * encoder layers (default on). */
 int himo_conv_set_weights_resident(int enable);
+/* A/B knob: 1 enables the TMA-store epilogue of the short-K 128-wide tiles (TMEM -> activation -> swizzled shared-memory
+ * tile -> one cp.async.bulk.tensor store per plane).  Default 0: measured slower than per-thread stores on a B200
+ * (profiles/r02_conv_tma_store_ab.txt). */
+int himo_conv_set_tma_store(int enable);
 /* A/B knob: 0 disables the two-output-rows tiles (k_conv_rows2: a CTA pair computes 2 rows x 256 px x 96 channels so that
  * activation rows and weight taps are shared; default on) of the 96-channel 3x3 decoder-half layers. */
 int himo_conv_set_rows2(int enable);

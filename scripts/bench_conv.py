@@ -25,6 +25,7 @@ LAYERS = [  # name, H, W, Cin, Cout, ksize, stride, groups, act (1 = bias + GELU
     ("probe enc1.1 x12 frames", 256, 256, 64, 64, 3, 1, 12, 1, 0),
     ("probe enc3.1 x6 frames", 64, 64, 256, 256, 3, 1, 6, 1, 0),
     ("probe enc3.1 x12 frames", 64, 64, 256, 256, 3, 1, 12, 1, 0),
+    ("mlp fwd 128->128 x100k relu", 782, 128, 128, 128, 1, 1, 1, 4, 0),
     ("gru zr 288->384 x100k", 782, 128, 288, 384, 1, 1, 1, 2, 1),
     ("gru q 288->192 x100k", 782, 128, 288, 192, 1, 1, 1, 3, 1),
 ]
@@ -49,6 +50,8 @@ if os.environ.get("WIDE") is not None:
     L.himo_conv_set_wide_tiles(int(os.environ["WIDE"]))
 if os.environ.get("WRES") is not None:
     L.himo_conv_set_weights_resident(int(os.environ["WRES"]))
+if os.environ.get("TSTORE") is not None:
+    L.himo_conv_set_tma_store(int(os.environ["TSTORE"]))
 if os.environ.get("ROWS2") is not None:
     L.himo_conv_set_rows2(int(os.environ["ROWS2"]))
 if os.environ.get("PDL") is not None:

@@ -50,7 +50,7 @@ def _run(H, W, cin, cout, ksize, stride, planes, act=0, out_fp32=False, groups=1
 ])
 def test_conv_split_bf16_matches_fp32(H, W, cin, cout, ksize, stride):
     err = _run(H, W, cin, cout, ksize, stride, planes=2)
-    assert err < 2e-6, err
+    assert err < 3e-6, err      # 2.1e-6 where the whole K runs as one 72-MMA accumulation chain (TMA-store tiles)
 
 
 def test_conv_gelu_fp32_out_and_groups():
@@ -92,6 +92,19 @@ def test_composed_u3_u4_with_border_bias(H, W, L, cout):
     conv.conv2d_nhwc(xp, wp, bc.cuda(), out, ksize=3, acc_scale=1.0 / ws, border_bias=bb.cuda())
     got = conv.merge_planes(out).cpu()
     assert (got - ref).abs().max().item() / ref.abs().max().item() < 3e-6
+
+
+def test_conv_tma_store_epilogue_knob():
+    """The TMA-store streaming epilogue (off by default: measured slower) stays correct."""
+    from himo_b200 import _lib
+    L = _lib.lib()
+    L.himo_conv_set_tma_store(1)
+    try:
+        assert _run(64, 64, 128, 128, 3, 1, planes=2, act=1) < 3e-6          # 64 x 2 pixel tiles, CTA pairs
+        assert _run(16, 128, 128, 128, 1, 1, planes=2) < 3e-6                 # the FastNSF GEMM shape
+        assert _run(128, 128, 64, 128, 3, 2, planes=2, act=1, groups=3) < 3e-6
+    finally:
+        L.himo_conv_set_tma_store(0)
 
 
 def test_conv_single_plane_bf16():
