@@ -15,9 +15,12 @@ from __future__ import annotations
 
 import os
 import pickle
+import threading
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
+
+_H5_WRITE_LOCK = threading.Lock()
 
 
 class FrameStore:
@@ -70,10 +73,24 @@ class NpyStore(FrameStore):
         os.replace(tmp, os.path.join(d, name + ".npy"))     # atomic: a re-run simply replaces the result
 
 
+def _h5_backend():
+    """h5py when it is importable (the reference's own library), else the self-contained subset codec `h5lite`
+    (superblock v0, symbol-table groups, contiguous datasets: what h5py writes by default and what the pipeline uses)."""
+    try:
+        import h5py
+        return h5py
+    except ImportError:
+        from . import h5lite
+        return h5lite
+
+
 class H5Store(FrameStore):
-    def __init__(self, directory: str):
-        import h5py  # noqa: F401  (fails loudly when absent)
+    """`<scene_id>.h5` files in the reference's schema: group `str(timestamp)` -> datasets (OSF/src/dataset.py:313-364 reads,
+    OSF/src/trainer.py:337-343 writes)."""
+
+    def __init__(self, directory: str, backend=None):
         self.dir = directory
+        self.h5 = backend or _h5_backend()
 
     def _path(self, scene):
         return os.path.join(self.dir, f"{scene}.h5")
@@ -82,42 +99,35 @@ class H5Store(FrameStore):
         return sorted(f[:-3] for f in os.listdir(self.dir) if f.endswith(".h5"))
 
     def timestamps(self, scene):
-        import h5py
-        with h5py.File(self._path(scene), "r") as f:
+        with self.h5.File(self._path(scene), "r") as f:
             return sorted(f.keys(), key=int)
 
     def has(self, scene, ts, name):
-        import h5py
-        with h5py.File(self._path(scene), "r") as f:
+        with self.h5.File(self._path(scene), "r") as f:
             return str(ts) in f and name in f[str(ts)]
 
     def names(self, scene, ts):
-        import h5py
-        with h5py.File(self._path(scene), "r") as f:
+        with self.h5.File(self._path(scene), "r") as f:
             return sorted(f[str(ts)].keys())
 
     def read(self, scene, ts, name):
-        import h5py
-        with h5py.File(self._path(scene), "r") as f:
+        with self.h5.File(self._path(scene), "r") as f:
             return f[str(ts)][name][:]
 
     def write(self, scene, ts, name, data):
-        import h5py
-        with h5py.File(self._path(scene), "a") as f:       # OSF/src/trainer.py:339-343
-            g = f.require_group(str(ts))
-            if name in g:
-                del g[name]
-            g.create_dataset(name, data=np.asarray(data))
+        with _H5_WRITE_LOCK:                                   # one writer per process (the runner's writer thread); scene
+            with self.h5.File(self._path(scene), "a") as f:     # sharding keeps processes out of each other's files
+                g = f.require_group(str(ts))                   # OSF/src/trainer.py:339-343
+                if name in g:
+                    del g[name]
+                g.create_dataset(name, data=np.asarray(data))
 
 
 def open_store(directory: str, prefer: Optional[str] = None) -> FrameStore:
     has_h5 = any(f.endswith(".h5") for f in os.listdir(directory)) if os.path.isdir(directory) else False
     if prefer == "npy" or not has_h5:
         return NpyStore(directory)
-    try:
-        return H5Store(directory)
-    except ImportError as e:
-        raise RuntimeError(f"{directory} holds .h5 scenes but h5py is not importable in this environment: {e}")
+    return H5Store(directory)
 
 
 def read_index(directory: str, name: str = "index_total.pkl") -> List[List]:

@@ -158,3 +158,24 @@ def test_instance_chamfer_on_device_equals_host_path(data_dir):
             assert x == y
     walk(a, b)
     assert len(a["av2"]["seflowpp_synth"]) > 0
+
+
+def test_save_into_h5_scene_files_equals_npy_store(tmp_path):
+    """(f)2: save.py on `.h5` scene files (the reference's on-disk contract, served by himo_b200.h5lite here) writes the same
+    flow as on the per-array store -- the result goes INTO the scene file next to `lidar` / `pose`, like trainer.py:337-343."""
+    from himo_b200 import h5lite
+    d_npy, d_h5 = str(tmp_path / "av2_npy"), str(tmp_path / "av2_h5")
+    os.makedirs(d_h5)
+    store.write_synthetic_dataset(d_npy, n_scenes=1, n_frames=4, n_points=3000, seed=9)
+    store.write_synthetic_dataset(d_h5, n_scenes=1, n_frames=4, n_points=3000, seed=9, store=store.H5Store(d_h5, backend=h5lite))
+    for d in (d_npy, d_h5):
+        _run(["save.py", "checkpoint=synthetic:4", f"dataset_path={d}", "res_name=seflowpp_synth"])
+    a, b = HDF5Dataset(d_npy, n_frames=3, vis_name="seflowpp_synth"), HDF5Dataset(d_h5, n_frames=3, vis_name="seflowpp_synth")
+    assert isinstance(b.store, store.H5Store)
+    for i in (1, 2):
+        assert np.array_equal(a[i]["seflowpp_synth"], b[i]["seflowpp_synth"])
+    (scene,) = b.store.scenes()
+    with h5lite.File(os.path.join(d_h5, scene + ".h5")) as f:
+        ts = f.keys()[1]
+        assert {"lidar", "pose", "ground_mask", "seflowpp_synth"} <= set(f[ts].keys())
+        assert f[ts]["seflowpp_synth"].dtype == np.float32 and f[ts]["seflowpp_synth"].shape[1] == 3
