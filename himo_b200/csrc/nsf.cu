@@ -184,6 +184,8 @@ struct NsfBufs {
   float* gW0;                      // [128][3] + [128] bias
   float* gb;                       // [7][128] bias grads of layers 1..7 (scaled)
   float* small_part;               // [8][splits][128][4]: per split (delta_{l+1}^T x, delta_{l+1}^T 1)
+  uint32_t* relu_mask[kNsfLayers]; // relu_mask[l], l = 1..7: [n_pad][4] bit j of word c = (h_l[32 c + j] > 0), written by the fused
+                                   // forward chain and read by the fused dX chain instead of the 50 MB activation tensor
   NsfCtl* ctl;
   float grad_scale;                // power of two S; every backward tensor carries S/N instead of 1/N
 };
@@ -605,6 +607,265 @@ k_nsf_dw(const __grid_constant__ DwMaps maps, const int* __restrict__ stop_flag,
   if (warp == 1) umma::tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------ fused layer chains: k_mlp_chain
+// The seven 128x128 hidden layers as ONE persistent kernel per direction instead of seven GEMM launches.  Unfused, every
+// layer moved its 128-point tile through the SM three times (64 KB of activations + 64 KB of weights in, 64 KB out, for
+// 768 cycles of MMA time: bound by SM<->L2 bytes).  Here a CTA pair (cta_group::2) owns 256 points for the
+// whole chain, exactly like the fused ConvGRU decoder (csrc/decfused.cu):
+//   * the activation tile lives in shared memory as split-fp16 planes in the K-major 64-byte-swizzled layout tcgen05.mma
+//     reads (4 chunks x 2 planes x 8 KB); the epilogue warps rewrite it in place with the next layer's activations;
+//   * the same tile is handed to TMA as-is (cp.async.bulk.tensor store, 8 per layer) to put h_{l+1} / delta_l into HBM for
+//     the weight-gradient kernel -- no per-thread global stores;
+//   * weights stream through an 8-stage TMA ring (one 32-channel k-chunk per stage, each CTA half of the 128 rows);
+//   * DIR 0 (forward): prologue = layer 0 on CUDA cores (h_1 = relu(W0 x + b0)); epilogue = bias + ReLU, and one bit per
+//     activation goes to relu_mask[l] (16 bytes per point per layer);
+//   * DIR 1 (backward, dX): prologue = TMA load of delta_8; layers 7..1 with the transposed weights; epilogue = the ReLU
+//     mask read back from those bits (instead of re-reading the 50 MB activation tensor per layer).
+// One accumulator (hi*hi and cross terms together: chains are 24 MMAs), 128 TMEM columns.
+constexpr int kChThreads = 320;
+constexpr int kChTile = 128 * 64;                      // one 32-channel plane tile of 128 rows: 8 KB
+constexpr int kChT = 4 * 2 * kChTile;                  // activation tile: 64 KB
+constexpr int kChWStage = 2 * 64 * 64;                 // one k-chunk of one layer, this CTA's 64 rows, both planes: 8 KB
+constexpr int kChWStages = 8;
+constexpr int kChOffW = kChT;
+constexpr int kChOffBar = kChOffW + kChWStages * kChWStage;
+constexpr int kChOffConst = kChOffBar + 256;
+constexpr int kChConstFloats = 7 * 128 + 384 + 128;
+constexpr int kChTotal = kChOffConst + kChConstFloats * 4 + 1024;
+
+struct ChainMaps { CUtensorMap w[kNsfLayers]; CUtensorMap act[kNsfLayers + 1]; };   // w[1..7]; act[l] = H[l] (DIR 0) / DL[l] (DIR 1)
+
+struct ChainParams {
+  int n_pair_tiles;
+  const float* params;             // fp32 master parameters (biases, W0)
+  const float4* x4;
+  uint32_t* mask[kNsfLayers];      // relu_mask[1..7]
+  float acc_scale;
+  const int* stop_flag;
+};
+
+__device__ __forceinline__ uint32_t ch_swz(int row, int j) { return (uint32_t)(row * 64 + ((j ^ ((row >> 1) & 3)) << 4)); }
+__device__ __forceinline__ void ch_store16(uint8_t* tile_hi, uint8_t* tile_lo, int row, int j0, const float* v) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma::pack_split2(v[u * 8 + 2 * k], v[u * 8 + 2 * k + 1], true, hi[k], lo[k]);
+    *(uint4*)(tile_hi + ch_swz(row, j0 + u)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *(uint4*)(tile_lo + ch_swz(row, j0 + u)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(kChThreads, 1)
+k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sT = smem;
+  uint8_t* sW = smem + kChOffW;
+  uint64_t* w_full = (uint64_t*)(smem + kChOffBar);      // [8]
+  uint64_t* w_empty = w_full + kChWStages;                // [8]
+  uint64_t* t_ready = w_empty + kChWStages;               // activation tile holds the next layer's input (2 arrivals: one per CTA)
+  uint64_t* t_tma = t_ready + 1;                          // DIR 1: delta_8 landed (tx, both CTAs)
+  uint64_t* t_free = t_tma + 1;                           // DIR 1: this CTA's tile may be overwritten by the next TMA load
+  uint64_t* acc_full = t_free + 1;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(acc_full + 1);
+  float* c_bias = (float*)(smem + kChOffConst);          // [7][128] biases of layers 1..7
+  float* c_w0 = c_bias + 7 * 128;                         // [128][3]
+  float* c_b0 = c_w0 + 384;                               // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (*p.stop_flag) return;
+  const uint32_t cta_rank = umma::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int n_workers = (int)(gridDim.x >> 1), worker = (int)(blockIdx.x >> 1);
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kChWStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
+    umma::mbar_init(t_ready, 2); umma::mbar_init(t_tma, 1); umma::mbar_init(t_free, 1); umma::mbar_init(acc_full, 1);
+    umma::fence_barrier_init();
+  } else if (warp == 1) {
+    umma::tmem_alloc_2cta(tmem_ptr_smem, 128);
+  }
+  if (DIR == 0) {
+    for (int i = threadIdx.x; i < 7 * 128; i += kChThreads) {
+      const int l = 1 + i / 128;
+      c_bias[i] = p.params[nsf_off_b(l) + (i & 127)];
+    }
+    for (int i = threadIdx.x; i < 384; i += kChThreads) c_w0[i] = p.params[nsf_off_w(0) + i];
+    for (int i = threadIdx.x; i < 128; i += kChThreads) c_b0[i] = p.params[nsf_off_b(0) + i];
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // layer order: DIR 0: l = 1..7 (input h_l, output h_{l+1});  DIR 1: l = 7..1 (input delta_{l+1}, output delta_l)
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    uint32_t git = 0;
+    int tc = 0;
+    for (int tile = worker; tile < p.n_pair_tiles; tile += n_workers, ++tc) {
+      if (DIR == 1) {
+        const int row0 = (tile * 2 + (int)cta_rank) * 128;
+        if (tc > 0) umma::mbar_wait(t_free, (uint32_t)((tc - 1) & 1));      // own tile: last stores have read it
+        const uint32_t fb = umma::mapa_u32(umma::smem_u32(t_tma), 0);
+        if (umma::elect_one()) {
+          if (leader) umma::mbar_arrive_expect_tx(t_tma, (uint32_t)(2 * kChT));
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+              umma::tma_load_3d_2cta(sT + (c * 2 + pl) * kChTile, &maps.act[kNsfLayers], fb, c * 32, row0, pl);
+        }
+        __syncwarp();
+      }
+      for (int k = 0; k < 7; ++k) {
+        const int l = DIR == 0 ? 1 + k : 7 - k;
+        for (int c = 0; c < 4; ++c, ++git) {
+          const int s = git % kChWStages;
+          umma::mbar_wait(&w_empty[s], ((git / kChWStages) & 1) ^ 1);
+          const uint32_t fb = umma::mapa_u32(umma::smem_u32(&w_full[s]), 0);
+          uint8_t* dst = sW + s * kChWStage;
+          if (umma::elect_one()) {
+            if (leader) umma::mbar_arrive_expect_tx(&w_full[s], (uint32_t)(2 * kChWStage));
+            umma::tma_load_3d_2cta(dst, &maps.w[l], fb, c * 32, (int)cta_rank * 64, 0);
+            umma::tma_load_3d_2cta(dst + 64 * 64, &maps.w[l], fb, c * 32, (int)cta_rank * 64, 1);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===================== MMA issuer (leader CTA) =====================
+      constexpr uint32_t idesc = umma::idesc_f16kind_f32(256, 128, 0u, 0u);
+      const uint32_t t_addr = umma::smem_u32(sT);
+      uint32_t git = 0, nready = 0;
+      int tc = 0;
+      for (int tile = worker; tile < p.n_pair_tiles; tile += n_workers, ++tc) {
+        for (int k = 0; k < 7; ++k) {
+          if (DIR == 1 && k == 0) umma::mbar_wait(t_tma, (uint32_t)(tc & 1));
+          else { umma::mbar_wait(t_ready, nready & 1); ++nready; }
+          umma::tc_fence_after();
+          for (int c = 0; c < 4; ++c, ++git) {
+            const int s = git % kChWStages;
+            umma::mbar_wait(&w_full[s], (git / kChWStages) & 1);
+            umma::tc_fence_after();
+            if (umma::elect_one()) {
+              const uint32_t a_hi = t_addr + (c * 2) * kChTile, a_lo = a_hi + kChTile;
+              const uint32_t b_hi = umma::smem_u32(sW + s * kChWStage), b_lo = b_hi + 64 * 64;
+              const uint64_t dah = umma::smem_desc_kmajor<64>(a_hi), dal = umma::smem_desc_kmajor<64>(a_lo);
+              const uint64_t dbh = umma::smem_desc_kmajor<64>(b_hi), dbl = umma::smem_desc_kmajor<64>(b_lo);
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint64_t koff = (uint64_t)(kk * 32 >> 4);
+                umma::mma_bf16_ss_2cta(tmem_base, dah + koff, dbl + koff, idesc, (c == 0 && kk == 0) ? 0u : 1u);
+                umma::mma_bf16_ss_2cta(tmem_base, dal + koff, dbh + koff, idesc, 1u);
+                umma::mma_bf16_ss_2cta(tmem_base, dah + koff, dbh + koff, idesc, 1u);
+              }
+              umma::mma_commit_2cta(&w_empty[s]);
+            }
+            __syncwarp();
+          }
+          if (umma::elect_one()) umma::mma_commit_2cta(acc_full);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps: layer-0 prologue (DIR 0), then one in-place epilogue per layer =====================
+    const int q = warp & 3, half = (warp - 2) >> 2, row = q * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t a_t_ready = umma::mapa_u32(umma::smem_u32(t_ready), 0);
+    const bool issuer = warp == 2 && lane == 0;
+    uint32_t nacc = 0;
+    int tc = 0;
+    auto publish = [&](const CUtensorMap* tm, int row0) {      // tile complete in shared memory: release it to MMA / TMA
+      umma::tc_fence_before();
+      umma::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (issuer) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) umma::tma_store_3d(tm, sT + (c * 2 + pl) * kChTile, c * 32, row0, pl);
+        umma::tma_store_commit();
+      }
+    };
+    for (int tile = worker; tile < p.n_pair_tiles; tile += n_workers, ++tc) {
+      const int row0 = (tile * 2 + (int)cta_rank) * 128;
+      const long long grow = (long long)row0 + row;
+      if (DIR == 0) {
+        // ---- layer 0: h_1 = relu(W0 x + b0), 64 channels per thread, straight into the operand tile
+        if (issuer) umma::tma_store_wait_read();                 // the previous tile's last stores have read the tile
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float4 x = p.x4[grow];
+        uint32_t mbits[2] = {0u, 0u};
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = half * 64 + g * 16;
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ch = col + j;
+            float t = c_w0[ch * 3] * x.x;
+            t = fmaf(c_w0[ch * 3 + 1], x.y, t);
+            t = fmaf(c_w0[ch * 3 + 2], x.z, t);
+            v[j] = fmaxf(t + c_b0[ch], 0.f);
+            if (v[j] > 0.f) mbits[g >> 1] |= 1u << ((g & 1) * 16 + j);
+          }
+          const int c = col >> 5;
+          ch_store16(sT + (c * 2) * kChTile, sT + (c * 2 + 1) * kChTile, row, (g & 1) * 2, v);
+        }
+        *(uint2*)(p.mask[1] + grow * 4 + half * 2) = make_uint2(mbits[0], mbits[1]);
+        publish(&maps.act[1], row0);
+        if (issuer) umma::mbar_arrive_cluster(a_t_ready);
+      }
+      for (int k = 0; k < 7; ++k, ++nacc) {
+        const int l = DIR == 0 ? 1 + k : 7 - k;
+        umma::mbar_wait(acc_full, nacc & 1);
+        umma::tc_fence_after();
+        if (issuer) umma::tma_store_wait_read();                 // the stores of the previous layer have read the tile
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        uint32_t mbits[2] = {0u, 0u};
+        if (DIR == 1) {
+          const uint2 mm = *(const uint2*)(p.mask[l] + grow * 4 + half * 2);
+          mbits[0] = mm.x; mbits[1] = mm.y;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = half * 64 + g * 16;
+          uint32_t acc[16];
+          umma::tmem_ld_32x16(tlane + (uint32_t)col, acc);
+          umma::tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (DIR == 0) {
+              v[j] = fmaxf(__fmaf_rn(__uint_as_float(acc[j]), p.acc_scale, c_bias[(l - 1) * 128 + col + j]), 0.f);
+              if (v[j] > 0.f) mbits[g >> 1] |= 1u << ((g & 1) * 16 + j);
+            } else {
+              const float t = __uint_as_float(acc[j]) * p.acc_scale;
+              v[j] = ((mbits[g >> 1] >> ((g & 1) * 16 + j)) & 1u) ? t : 0.f;
+            }
+          }
+          const int c = col >> 5;
+          ch_store16(sT + (c * 2) * kChTile, sT + (c * 2 + 1) * kChTile, row, (g & 1) * 2, v);
+        }
+        if (DIR == 0 && l < 7) *(uint2*)(p.mask[l + 1] + grow * 4 + half * 2) = make_uint2(mbits[0], mbits[1]);
+        publish(&maps.act[DIR == 0 ? l + 1 : l], row0);
+        if (k < 6) { if (issuer) umma::mbar_arrive_cluster(a_t_ready); }
+        else if (DIR == 1 && issuer) { umma::tma_store_wait_read(); umma::mbar_arrive(t_free); }
+      }
+    }
+    if (issuer) umma::tma_store_wait_all();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync();
+  if (warp == 1) umma::tmem_dealloc_2cta(tmem_base, 128);
+}
+
 // bias gradients and dW_0 from the split partials of k_nsf_dw: column 3 = delta^T 1, columns 0..2 = delta_1^T x
 __global__ void __launch_bounds__(128)
 k_nsf_small_final(NsfBufs b, int splits) {
@@ -816,13 +1077,15 @@ struct NsfLayout {
 
 static size_t nsf_layout(int n_max, int planes, NsfLayout* L, void* base) {
   Arena A(base, (size_t)-1);
-  const int n_pad = ceil_div(n_max > 0 ? n_max : 1, 128) * 128;
+  const int n_pad = ceil_div(n_max > 0 ? n_max : 1, 256) * 256;   // k_mlp_chain works on 256-point CTA-pair tiles
   const size_t act = (size_t)planes * n_pad * 128;
   NsfLayout l;
   l.b.x4 = A.take<float4>(n_pad);
   l.b.x16 = A.take<__nv_bfloat16>((size_t)planes * n_pad * 32);
   for (int k = 1; k <= kNsfLayers; ++k) { l.b.H[k] = A.take<__nv_bfloat16>(act); l.b.DL[k] = A.take<__nv_bfloat16>(act); }
   l.b.H[0] = l.b.DL[0] = nullptr;
+  l.b.relu_mask[0] = nullptr;
+  for (int k = 1; k < kNsfLayers; ++k) l.b.relu_mask[k] = A.take<uint32_t>((size_t)n_pad * 4);
   l.b.params = A.take<float>(kNsfParams);
   l.ad.m = A.take<float>(kNsfParams);
   l.ad.v = A.take<float>(kNsfParams);
@@ -852,9 +1115,56 @@ static size_t nsf_layout(int n_max, int planes, NsfLayout* L, void* base) {
 
 static int nsf_gemm(const himo_conv_desc& d, cudaStream_t stream) { return himo_conv2d_nhwc(&d, stream); }
 
-// h_1 = relu(W0 x + b0) on CUDA cores, then h_{l+1} = relu(W_l h_l + b_l), l = 1..7, on the tcgen05 GEMM
+static int g_nsf_fused = 1;
+static PFN_cuTensorMapEncodeTiled nsf_encode_fn();
+// [planes][rows][C] 16-bit tensor, box = (32 channels, box_rows, 1 plane), 64-byte swizzle
+static int nsf_map(CUtensorMap* m, const void* base, int planes, long long rows, int C, int box_rows) {
+  PFN_cuTensorMapEncodeTiled enc = nsf_encode_fn();
+  if (!enc) return HIMO_ERR_UNSUPPORTED;
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)rows * C * 2};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? HIMO_OK : HIMO_ERR_ARG;
+}
+
+template <int DIR>
+static int nsf_launch_chain(const NsfBufs& b, const NsfAdamArgs& ad, cudaStream_t stream) {
+  ChainMaps maps;
+  for (int l = 1; l < kNsfLayers; ++l) HIMO_RET(nsf_map(&maps.w[l], DIR == 0 ? ad.Wp[l] : ad.WpT[l], 2, 128, 128, 64));
+  maps.w[0] = maps.w[1];
+  for (int l = 1; l <= kNsfLayers; ++l) HIMO_RET(nsf_map(&maps.act[l], DIR == 0 ? b.H[l] : b.DL[l], 2, b.n_pad, 128, 128));
+  maps.act[0] = maps.act[1];
+  ChainParams p;
+  p.n_pair_tiles = b.n_pad / 256;
+  p.params = b.params; p.x4 = b.x4; p.acc_scale = 1.0f / kNsfWScale; p.stop_flag = &b.ctl->stop;
+  for (int l = 0; l < kNsfLayers; ++l) p.mask[l] = b.relu_mask[l];
+  static bool configured_dev[64] = {};
+  int dev_ = 0;
+  HIMO_CUDA_RET(cudaGetDevice(&dev_));
+  if (!configured_dev[dev_ & 63]) {
+    HIMO_CUDA_RET(cudaFuncSetAttribute(k_mlp_chain<DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChTotal));
+    configured_dev[dev_ & 63] = true;
+  }
+  const int pairs = p.n_pair_tiles < kNumSMs / 2 ? p.n_pair_tiles : kNumSMs / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pairs * 2); cfg.blockDim = dim3(kChThreads); cfg.dynamicSmemBytes = kChTotal; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  HIMO_CUDA_RET(cudaLaunchKernelEx(&cfg, k_mlp_chain<DIR>, maps, p));
+  HIMO_LAUNCH_RET();
+  return HIMO_OK;
+}
+
+// h_1 = relu(W0 x + b0), then h_{l+1} = relu(W_l h_l + b_l), l = 1..7: one fused chain launch in the split-plane mode
+// (k_mlp_chain<0>), else layer 0 on CUDA cores + seven launches of the tcgen05 GEMM
 static int nsf_forward_hidden(const NsfBufs& b, const NsfAdamArgs& ad, cudaStream_t stream) {
   const int P = b.planes, n_pad = b.n_pad;
+  if (P == 2 && g_nsf_fused) return nsf_launch_chain<0>(b, ad, stream);
   const float wscale = P == 2 ? 1.0f / kNsfWScale : 1.0f;
   k_nsf_l0_fwd<<<min(n_pad / kL0Pts, kNumSMs * 8), 256, 0, stream>>>(b); HIMO_LAUNCH_RET();
   for (int l = 1; l < kNsfLayers; ++l) {
@@ -898,7 +1208,8 @@ static int nsf_backward_hidden(const NsfBufs& b, const NsfAdamArgs& ad, float* d
                                cudaStream_t stream) {
   const int P = b.planes, n_pad = b.n_pad;
   const float wscale = P == 2 ? 1.0f / kNsfWScale : 1.0f;
-  for (int l = kNsfLayers - 1; l >= 1; --l) {
+  if (P == 2 && g_nsf_fused) HIMO_RET(nsf_launch_chain<1>(b, ad, stream));
+  else for (int l = kNsfLayers - 1; l >= 1; --l) {
     himo_conv_desc q = {};
     q.in = b.DL[l + 1]; q.in_planes = P; q.in_plane_stride = b.ps; q.H_in = n_pad / 128; q.W_in = 128;
     q.Cin_total = 128; q.Cin = 128; q.wgt = ad.WpT[l]; q.bias = nullptr; q.Cout = 128; q.ksize = 1; q.stride = 1;
@@ -931,7 +1242,7 @@ struct NsfCall { NsfLayout L; NsfBufs b; NsfAdamArgs ad; int head_blocks, k_spli
 static int nsf_call_setup(void* workspace, size_t workspace_bytes, int n_max, int planes, int n, float lr, NsfCall* c) {
   if (!workspace || (planes != 1 && planes != 2) || n <= 0 || n > n_max) return HIMO_ERR_ARG;
   if (nsf_layout(n_max, planes, &c->L, workspace) > workspace_bytes) return HIMO_ERR_WORKSPACE;
-  const int n_pad = ceil_div(n, 128) * 128;
+  const int n_pad = ceil_div(n, 256) * 256;
   c->b = c->L.b;
   c->b.n = n; c->b.n_pad = n_pad; c->b.planes = planes; c->b.ps = (long long)n_pad * 128;
   int e = 0; while ((1 << e) < n) ++e;
@@ -950,6 +1261,9 @@ static int nsf_call_setup(void* workspace, size_t workspace_bytes, int n_max, in
 }  // namespace himo
 
 using namespace himo;
+
+// A/B knob: 0 runs the hidden layers as 14 GEMM launches per iteration instead of the two fused chain kernels.
+extern "C" int himo_nsf_set_fused(int enable) { g_nsf_fused = enable ? 1 : 0; return HIMO_OK; }
 
 extern "C" size_t himo_nsf_workspace_bytes(int n_max, int planes) {
   if (n_max < 0 || (planes != 1 && planes != 2)) return 0;
@@ -1014,7 +1328,7 @@ extern "C" int himo_nsf_optimize(const himo_nsf_desc* d, void* stream_) {
   if (P != 1 && P != 2) return HIMO_ERR_ARG;
   NsfLayout L;
   if (nsf_layout(d->n_max, P, &L, d->workspace) > d->workspace_bytes || d->n > d->n_max) return HIMO_ERR_WORKSPACE;
-  const int n = d->n, n_pad = ceil_div(n, 128) * 128;
+  const int n = d->n, n_pad = ceil_div(n, 256) * 256;
   NsfBufs b = L.b;
   b.n = n; b.n_pad = n_pad; b.planes = P; b.ps = (long long)n_pad * 128;
   int e = 0; while ((1 << e) < n) ++e;

@@ -361,6 +361,9 @@ typedef struct himo_nsf_desc {
   void* workspace; size_t workspace_bytes;
 } himo_nsf_desc;
 size_t himo_nsf_workspace_bytes(int n_max, int planes);
+/* A/B knob: 0 runs the seven hidden layers of the prior as GEMM launches (7 forward + 7 backward per iteration) instead of
+ * the two fused chain kernels (k_mlp_chain: a 256-point tile stays in shared memory across the layers; default 1). */
+int himo_nsf_set_fused(int enable);
 int himo_nsf_volume_geometry(const float* pc0, int n0, const float* pc1, int n1, float grid_factor,
                              float* lo_host, int32_t* dims_host, void* workspace, void* stream);
 int himo_nsf_dt_build(const float* pc1, int n1, const float* lo, const int32_t* dims, float grid_factor,
