@@ -183,7 +183,8 @@ struct NsfBufs {
   float* head_part;                // [head_blocks][kHeadPart]
   float* gW0;                      // [128][3] + [128] bias
   float* gb;                       // [7][128] bias grads of layers 1..7 (scaled)
-  float* small_part;               // [8][splits][128][4]: per split (delta_{l+1}^T x, delta_{l+1}^T 1)
+  float* small_part;               // [9][splits][128][4]: per split (delta_{l+1}^T x, delta_{l+1}^T 1) for l = 0..7, h_8^T dflow for l = 8
+  __nv_bfloat16* d16;              // [planes][n_pad][32]: (dflow_x, dflow_y, dflow_z, 0...) per point, scaled like the deltas
   uint32_t* relu_mask[kNsfLayers]; // relu_mask[l], l = 1..7: [n_pad][4] bit j of word c = (h_l[32 c + j] > 0), written by the fused
                                    // forward chain and read by the fused dX chain instead of the 50 MB activation tensor
   NsfCtl* ctl;
@@ -262,7 +263,7 @@ __device__ __forceinline__ void load_split8(const __nv_bfloat16* p, long long ps
 }
 
 constexpr int kHeadThreads = 128;
-constexpr int kHeadPart = 3 * 128 + 3 + 1;   // dW8, db8, loss
+constexpr int kHeadPart = 4;                 // per-block partial sums: db8 [3], loss
 
 // output layer of point i: flow = W8 h8 + b8 (W8 staged in shared memory)
 __device__ __forceinline__ void head_flow(const NsfBufs& b, const float* sW8, int i, float f[3]) {
@@ -282,51 +283,43 @@ __device__ __forceinline__ void head_flow(const NsfBufs& b, const float* sW8, in
   f[0] = f0 + __ldg(b8); f[1] = f1 + __ldg(b8 + 1); f[2] = f2 + __ldg(b8 + 2);
 }
 
-// backward through the output layer and the ReLU of h8: delta_8 = (d W8) * relu'(h8) -> DL[8]; per-block partial sums
-// of dW8 [3][128], db8 [3] and `extra` (the loss for FastNSF) in head_part (fixed shuffle trees => deterministic)
+// backward through the output layer and the ReLU of h8: delta_8 = (d W8) * relu'(h8) -> DL[8]; d -> d16 (dW8 = d^T h8 is
+// then one more item of k_nsf_dw: the 384 per-block shuffle reductions this kernel used to do took 60 of its 95 us);
+// per-block partial sums of db8 [3] and `extra` (the loss for FastNSF) in head_part (fixed shuffle tree => deterministic)
 __device__ __forceinline__ void head_backward(const NsfBufs& b, const float* sW8, int i, float d0, float d1, float d2,
-                                              float extra, float (*red_w)[3][128], float (*red)[4]) {
+                                              float extra, float (*red)[4]) {
   float* part = b.head_part + (size_t)blockIdx.x * kHeadPart;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool in_pad = i < b.n_pad;
   const bool split = b.planes == 2;
   const __nv_bfloat16* h8 = b.H[8] + (long long)i * 128;
-  for (int j0 = 0; j0 < 128; j0 += 8) {
-    float h[8], dhv[8];
-    if (in_pad) load_split8(h8 + j0, b.ps, b.planes, h);
-    else {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) h[u] = 0.f;
+  if (in_pad) {
+    uint32_t hi[2], lo[2];
+    umma::pack_split2(d0, d1, split, hi[0], lo[0]);
+    umma::pack_split2(d2, 0.f, split, hi[1], lo[1]);
+    uint4* q0 = (uint4*)(b.d16 + (size_t)i * 32);
+    q0[0] = make_uint4(hi[0], hi[1], 0u, 0u); q0[1] = make_uint4(0u, 0u, 0u, 0u);
+    q0[2] = make_uint4(0u, 0u, 0u, 0u); q0[3] = make_uint4(0u, 0u, 0u, 0u);
+    if (split) {
+      uint4* q1 = (uint4*)(b.d16 + (size_t)b.n_pad * 32 + (size_t)i * 32);
+      q1[0] = make_uint4(lo[0], lo[1], 0u, 0u); q1[1] = make_uint4(0u, 0u, 0u, 0u);
+      q1[2] = make_uint4(0u, 0u, 0u, 0u); q1[3] = make_uint4(0u, 0u, 0u, 0u);
     }
+    for (int j0 = 0; j0 < 128; j0 += 8) {
+      float h[8], dhv[8];
+      load_split8(h8 + j0, b.ps, b.planes, h);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u;
-      float dh = fmaf(d2, sW8[256 + j], fmaf(d1, sW8[128 + j], d0 * sW8[j]));
-      if (!(h[u] > 0.f)) dh = 0.f;
-      dhv[u] = dh;
-      float a0 = d0 * h[u], a1 = d1 * h[u], a2 = d2 * h[u];
-#pragma unroll
-      for (int sft = 16; sft > 0; sft >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, sft);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
-        a2 += __shfl_xor_sync(0xffffffffu, a2, sft);
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u;
+        const float dh = fmaf(d2, sW8[256 + j], fmaf(d1, sW8[128 + j], d0 * sW8[j]));
+        dhv[u] = h[u] > 0.f ? dh : 0.f;
       }
-      if (lane == 0) { red_w[warp][0][j] = a0; red_w[warp][1][j] = a1; red_w[warp][2][j] = a2; }
-    }
-    if (in_pad) {
-      uint32_t hi[4], lo[4];
+      uint32_t ph[4], pl[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) umma::pack_split2(dhv[2 * u], dhv[2 * u + 1], split, hi[u], lo[u]);
-      *(uint4*)(b.DL[8] + (long long)i * 128 + j0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      if (split) *(uint4*)(b.DL[8] + b.ps + (long long)i * 128 + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      for (int u = 0; u < 4; ++u) umma::pack_split2(dhv[2 * u], dhv[2 * u + 1], split, ph[u], pl[u]);
+      *(uint4*)(b.DL[8] + (long long)i * 128 + j0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      if (split) *(uint4*)(b.DL[8] + b.ps + (long long)i * 128 + j0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < 384; t += kHeadThreads) {
-    const int k = t >> 7, j = t & 127;
-    float sacc = 0.f;
-    for (int wv = 0; wv < kHeadThreads / 32; ++wv) sacc += red_w[wv][k][j];
-    part[k * 128 + j] = sacc;
   }
   float a0 = d0, a1 = d1, a2 = d2, a3 = extra;
 #pragma unroll
@@ -341,7 +334,7 @@ __device__ __forceinline__ void head_backward(const NsfBufs& b, const float* sW8
   if (threadIdx.x < 4) {
     float s = 0.f;
     for (int wv = 0; wv < kHeadThreads / 32; ++wv) s += red[wv][threadIdx.x];
-    part[384 + threadIdx.x] = s;
+    part[threadIdx.x] = s;
   }
 }
 
@@ -351,7 +344,6 @@ __global__ void __launch_bounds__(kHeadThreads)
 k_nsf_head(NsfBufs b, const float* __restrict__ D, NsfVol vol) {
   if (b.ctl->stop) return;
   __shared__ float red[kHeadThreads / 32][4];
-  __shared__ float red_w[kHeadThreads / 32][3][128];
   __shared__ float sW8[384];
   for (int t = threadIdx.x; t < 384; t += kHeadThreads) sW8[t] = b.params[nsf_off_w(8) + t];
   __syncthreads();
@@ -398,7 +390,7 @@ k_nsf_head(NsfBufs b, const float* __restrict__ D, NsfVol vol) {
   const float d0 = live ? gx * pass[0] * sN : 0.f, d1 = live ? gy * pass[1] * sN : 0.f, d2 = live ? gz * pass[2] * sN : 0.f;
   if (!live) val = 0.f;
   if (live) *(float4*)(b.flow + 4 * (size_t)i) = make_float4(f0, f1, f2, val);
-  head_backward(b, sW8, i, d0, d1, d2, val, red_w, red);
+  head_backward(b, sW8, i, d0, d1, d2, val, red);
 }
 
 // loss reduction + best-flow bookkeeping + EarlyStopping.step (nsfp_module.py:65-82), single thread.
@@ -408,7 +400,7 @@ __global__ void k_nsf_control(NsfBufs b, int head_blocks, float min_delta, int p
   const int stopped = c->stop;
   double s = 0.0;
   if (!stopped)   // 32 strided partial sums + a fixed shuffle tree (deterministic)
-    for (int k = threadIdx.x; k < head_blocks; k += 32) s += (double)b.head_part[(size_t)k * kHeadPart + 387];
+    for (int k = threadIdx.x; k < head_blocks; k += 32) s += (double)b.head_part[(size_t)k * kHeadPart + 3];
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
   if (threadIdx.x != 0) return;
@@ -457,7 +449,7 @@ constexpr int kDwBarOffset = kDwStages * kDwStageB;
 constexpr int kDwTotal = kDwBarOffset + 256 + 1024;
 constexpr int kDwThreads = 192;                        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 
-struct DwMaps { CUtensorMap delta[kNsfLayers + 1]; CUtensorMap h[kNsfLayers]; CUtensorMap x; };   // delta[1..8], h[1..7]
+struct DwMaps { CUtensorMap delta[kNsfLayers + 1]; CUtensorMap h[kNsfLayers + 1]; CUtensorMap x; CUtensorMap d; };   // delta[1..8], h[1..8]
 
 __device__ __forceinline__ uint64_t dw_desc_mn(uint32_t addr) {   // MN-major, SWIZZLE_64B: LBO = chunk stride, SBO = 8 rows
   uint64_t d = 0;
@@ -500,26 +492,30 @@ k_nsf_dw(const __grid_constant__ DwMaps maps, const int* __restrict__ stop_flag,
   // TMEM columns: buffer k: dW accumulator [k*144, +128), small accumulator [k*144 + 128, +16)
   if (warp == 0) {
     uint32_t git = 0;
-    for (int l = 0; l < kNsfLayers; ++l) {
+    for (int l = 0; l <= kNsfLayers; ++l) {
       for (int st = 0; st < n_stage; ++st, ++git) {
         const int s = git % kDwStages;
         umma::mbar_wait(&empty_bar[s], ((git / kDwStages) & 1) ^ 1);
         if (umma::elect_one()) {
           uint8_t* dst = smem + s * kDwStageB;
           const int pt = p0 + st * kDwKT;
-          umma::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(planes * (4 * kDwChunkB * (l > 0 ? 2 : 1) + kDwChunkB)));
+          // item l < 8: A = delta_{l+1}, B = h_l (l > 0), small B = (x, y, z, 1); item 8: A = h_8, small B = dflow (dW_8^T)
+          const bool big = l > 0 && l < kNsfLayers;
+          const CUtensorMap* mA = l < kNsfLayers ? &maps.delta[l + 1] : &maps.h[kNsfLayers];
+          const CUtensorMap* mS = l < kNsfLayers ? &maps.x : &maps.d;
+          umma::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(planes * (4 * kDwChunkB * (big ? 2 : 1) + kDwChunkB)));
           for (int pl = 0; pl < planes; ++pl)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              umma::tma_load_3d(dst + (pl * 4 + c) * kDwChunkB, &maps.delta[l + 1], &full_bar[s], c * 32, pt, pl);
-          if (l > 0) {
+              umma::tma_load_3d(dst + (pl * 4 + c) * kDwChunkB, mA, &full_bar[s], c * 32, pt, pl);
+          if (big) {
             for (int pl = 0; pl < planes; ++pl)
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 umma::tma_load_3d(dst + kDwOpB + (pl * 4 + c) * kDwChunkB, &maps.h[l], &full_bar[s], c * 32, pt, pl);
           }
           for (int pl = 0; pl < planes; ++pl)
-            umma::tma_load_3d(dst + 2 * kDwOpB + pl * kDwChunkB, &maps.x, &full_bar[s], 0, pt, pl);
+            umma::tma_load_3d(dst + 2 * kDwOpB + pl * kDwChunkB, mS, &full_bar[s], 0, pt, pl);
         }
         __syncwarp();
       }
@@ -531,7 +527,7 @@ k_nsf_dw(const __grid_constant__ DwMaps maps, const int* __restrict__ stop_flag,
     const uint32_t id_small = umma::idesc_f16kind_f32(128, 16, fmt, fmt) | kMN;
     const bool split = planes == 2;
     uint32_t git = 0;
-    for (int l = 0; l < kNsfLayers; ++l) {
+    for (int l = 0; l <= kNsfLayers; ++l) {
       const int buf = l & 1;
       umma::mbar_wait(&acc_empty[buf], ((l >> 1) & 1) ^ 1);
       umma::tc_fence_after();
@@ -547,7 +543,7 @@ k_nsf_dw(const __grid_constant__ DwMaps maps, const int* __restrict__ stop_flag,
             const uint32_t ko = (uint32_t)(k * 16 * 64);
             const uint64_t a_hi = dw_desc_mn(a0 + ko), a_lo = dw_desc_mn(a0 + 4 * kDwChunkB + ko);
             const uint32_t first = (st == 0 && k == 0) ? 0u : 1u;
-            if (l > 0) {
+            if (l > 0 && l < kNsfLayers) {
               const uint64_t b_hi = dw_desc_mn(b0 + ko), b_lo = dw_desc_mn(b0 + 4 * kDwChunkB + ko);
               umma::mma_bf16_ss(t_big, a_hi, b_hi, id_big, first);
               if (split) {
@@ -572,12 +568,12 @@ k_nsf_dw(const __grid_constant__ DwMaps maps, const int* __restrict__ stop_flag,
   } else {
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;                 // out feature (row of dW)
-    for (int l = 0; l < kNsfLayers; ++l) {
+    for (int l = 0; l <= kNsfLayers; ++l) {
       const int buf = l & 1;
       umma::mbar_wait(&acc_full[buf], (l >> 1) & 1);
       umma::tc_fence_after();
       const uint32_t t_big = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 144);
-      if (l > 0) {
+      if (l > 0 && l < kNsfLayers) {
         float* dst = dW_part + ((size_t)(l - 1) * splits + cta) * 16384 + (size_t)m * 128;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -832,12 +828,14 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           const uint2 mm = *(const uint2*)(p.mask[l] + grow * 4 + half * 2);
           mbits[0] = mm.x; mbits[1] = mm.y;
         }
+        uint32_t accs[4][16];                                   // all four loads in flight before ONE wait
+#pragma unroll
+        for (int g = 0; g < 4; ++g) umma::tmem_ld_32x16(tlane + (uint32_t)(half * 64 + g * 16), accs[g]);
+        umma::tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int col = half * 64 + g * 16;
-          uint32_t acc[16];
-          umma::tmem_ld_32x16(tlane + (uint32_t)col, acc);
-          umma::tmem_ld_wait();
+          const uint32_t* acc = accs[g];
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -866,20 +864,6 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   if (warp == 1) umma::tmem_dealloc_2cta(tmem_base, 128);
 }
 
-// bias gradients and dW_0 from the split partials of k_nsf_dw: column 3 = delta^T 1, columns 0..2 = delta_1^T x
-__global__ void __launch_bounds__(128)
-k_nsf_small_final(NsfBufs b, int splits) {
-  if (b.ctl->stop) return;
-  const int l = blockIdx.x, m = threadIdx.x;      // layer 0..7, feature
-  float t[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int s = 0; s < splits; ++s) {
-    const float4 v = *(const float4*)(b.small_part + (((size_t)l * splits + s) * 128 + m) * 4);
-    t[0] += v.x; t[1] += v.y; t[2] += v.z; t[3] += v.w;
-  }
-  if (l == 0) { b.gW0[m * 3] = t[0]; b.gW0[m * 3 + 1] = t[1]; b.gW0[m * 3 + 2] = t[2]; b.gW0[384 + m] = t[3]; }
-  else b.gb[(l - 1) * 128 + m] = t[3];
-}
-
 // ------------------------------------------------------------------------------ generic MLP entry points (NSFP)
 // The same 3 -> 128 x 8 -> 3 prior with the loss OUTSIDE: himo_mlp_forward returns the network output, the caller
 // (NSFP: truncated Chamfer of two networks, OSF/src/models/nsfp.py:48-72) computes any loss and hands d loss / d output
@@ -904,7 +888,6 @@ __global__ void __launch_bounds__(kHeadThreads)
 k_mlp_head_bwd(NsfBufs b, const float* __restrict__ d_out) {
   if (b.ctl->stop) return;
   __shared__ float red[kHeadThreads / 32][4];
-  __shared__ float red_w[kHeadThreads / 32][3][128];
   __shared__ float sW8[384];
   for (int t = threadIdx.x; t < 384; t += kHeadThreads) sW8[t] = b.params[nsf_off_w(8) + t];
   __syncthreads();
@@ -913,7 +896,7 @@ k_mlp_head_bwd(NsfBufs b, const float* __restrict__ d_out) {
   const float S = b.grad_scale;
   const float d0 = live ? d_out[3 * (size_t)i] * S : 0.f, d1 = live ? d_out[3 * (size_t)i + 1] * S : 0.f,
               d2 = live ? d_out[3 * (size_t)i + 2] * S : 0.f;
-  head_backward(b, sW8, i, d0, d1, d2, 0.f, red_w, red);
+  head_backward(b, sW8, i, d0, d1, d2, 0.f, red);
 }
 
 // d loss / d input = delta_1 W0 (the only path from the input: h1 = relu(W0 x + b0))
@@ -970,9 +953,10 @@ struct NsfAdamArgs {
   float* params; float* m; float* v;
   const float* dW_part;      // [7][splits][128][128]
   int splits;
-  const float* gb;           // [7][128]
-  const float* gW0;          // [128][3]
-  const float* gb0;          // [128]
+  const float* small_part;   // [9][splits][128][4] (k_nsf_dw): columns 0..2 = delta_1^T x (l = 0) / h_8^T dflow (l = 8), column 3 = bias gradient
+  const float* gb;           // unused (kept for layout stability)
+  const float* gW0;
+  const float* gb0;
   const float* head_part; int head_blocks;
   __nv_bfloat16* Wp[kNsfLayers];    // packed [P][128][128] weights of layers 1..7 (index l)
   __nv_bfloat16* WpT[kNsfLayers];   // packed transposes
@@ -993,11 +977,19 @@ k_nsf_adam(NsfAdamArgs a) {
     float g = 0.f;
     int layer = -1, r = 0, c = 0;
     bool is_w = false;
-    if (t < 384) { g = a.gW0[t]; }
-    else if (t < 512) { g = a.gb0[t - 384]; }
+    // every gradient is a sum over the `splits` point ranges of k_nsf_dw, added here in index order (deterministic)
+    auto small_sum = [&](int l, int m, int comp) {
+      const float* q = a.small_part + ((size_t)l * a.splits * 128 + m) * 4 + comp;
+      float acc = 0.f;
+      for (int s = 0; s < a.splits; ++s) acc += q[(size_t)s * 512];
+      return acc;
+    };
+    if (t < 384) { g = small_sum(0, t / 3, t % 3); }                       // dW0[m][c]
+    else if (t < 512) { g = small_sum(0, t - 384, 3); }                    // db0
+    else if (t >= nsf_off_b(8)) { continue; }                              // db8: the first warp of block 0, below
     else if (t >= nsf_off_w(8)) {
-      const int k = t - nsf_off_w(8);       // dW8 [3][128] then db8 [3]
-      for (int blk = 0; blk < a.head_blocks; ++blk) g += a.head_part[(size_t)blk * kHeadPart + k];
+      const int k = t - nsf_off_w(8);                                      // dW8[k / 128][k % 128] = (h_8^T dflow)[j][k]
+      g = small_sum(8, k & 127, k >> 7);
     } else {
       const int u = t - 512;
       layer = 1 + u / (128 * 128 + 128);
@@ -1007,7 +999,7 @@ k_nsf_adam(NsfAdamArgs a) {
         const float* p = a.dW_part + ((size_t)(layer - 1) * a.splits) * 16384 + w;
         for (int s = 0; s < a.splits; ++s) g += p[(size_t)s * 16384];
       } else {
-        g = a.gb[(layer - 1) * 128 + (w - 128 * 128)];
+        g = small_sum(layer, w - 128 * 128, 3);                            // db_l
       }
     }
     g *= a.inv_scale;
@@ -1021,6 +1013,24 @@ k_nsf_adam(NsfAdamArgs a) {
       const float scaled = a.planes == 2 ? pnew * kNsfWScale : pnew;
       umma::store_split(a.Wp[layer] + r * 128 + c, 16384, a.planes, scaled);
       umma::store_split(a.WpT[layer] + c * 128 + r, 16384, a.planes, scaled);
+    }
+  }
+  // db8 = sum over the head blocks of their partials: 32 strided sums + a fixed shuffle tree (a single thread walking the
+  // ~800 blocks was the longest chain of the kernel)
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    for (int k = 0; k < 3; ++k) {
+      float g = 0.f;
+      for (int blk = threadIdx.x; blk < a.head_blocks; blk += 32) g += a.head_part[(size_t)blk * kHeadPart + k];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) g += __shfl_xor_sync(0xffffffffu, g, d);
+      if (threadIdx.x == 0) {
+        const int t = nsf_off_b(8) + k;
+        g *= a.inv_scale;
+        const float m = a.beta1 * a.m[t] + (1.f - a.beta1) * g;
+        const float v = a.beta2 * a.v[t] + (1.f - a.beta2) * g * g;
+        a.m[t] = m; a.v[t] = v;
+        a.params[t] -= (a.lr / bc1) * (m / (sqrtf(v) / sqrtf(bc2) + a.eps));
+      }
     }
   }
 }
@@ -1082,6 +1092,7 @@ static size_t nsf_layout(int n_max, int planes, NsfLayout* L, void* base) {
   NsfLayout l;
   l.b.x4 = A.take<float4>(n_pad);
   l.b.x16 = A.take<__nv_bfloat16>((size_t)planes * n_pad * 32);
+  l.b.d16 = A.take<__nv_bfloat16>((size_t)planes * n_pad * 32);
   for (int k = 1; k <= kNsfLayers; ++k) { l.b.H[k] = A.take<__nv_bfloat16>(act); l.b.DL[k] = A.take<__nv_bfloat16>(act); }
   l.b.H[0] = l.b.DL[0] = nullptr;
   l.b.relu_mask[0] = nullptr;
@@ -1099,7 +1110,7 @@ static size_t nsf_layout(int n_max, int planes, NsfLayout* L, void* base) {
   l.k_split = 32 * ceil_div(n_pad, 32 * kNumSMs);
   l.splits = ceil_div(n_pad, l.k_split);
   l.dW_part = A.take<float>((size_t)7 * l.splits * 16384);
-  l.b.small_part = A.take<float>((size_t)8 * l.splits * 128 * 4);
+  l.b.small_part = A.take<float>((size_t)9 * l.splits * 128 * 4);
   for (int k = 1; k < kNsfLayers; ++k) {
     l.ad.Wp[k] = A.take<__nv_bfloat16>((size_t)planes * 16384);
     l.ad.WpT[k] = A.take<__nv_bfloat16>((size_t)planes * 16384);
@@ -1221,9 +1232,10 @@ static int nsf_backward_hidden(const NsfBufs& b, const NsfAdamArgs& ad, float* d
   DwMaps maps;
   for (int l = 1; l <= kNsfLayers; ++l) HIMO_RET(nsf_map_rows(&maps.delta[l], b.DL[l], P, n_pad, 128));
   maps.delta[0] = maps.delta[1];
-  for (int l = 1; l < kNsfLayers; ++l) HIMO_RET(nsf_map_rows(&maps.h[l], b.H[l], P, n_pad, 128));
+  for (int l = 1; l <= kNsfLayers; ++l) HIMO_RET(nsf_map_rows(&maps.h[l], b.H[l], P, n_pad, 128));
   maps.h[0] = maps.h[1];
   HIMO_RET(nsf_map_rows(&maps.x, b.x16, P, n_pad, 32));
+  HIMO_RET(nsf_map_rows(&maps.d, b.d16, P, n_pad, 32));
   static bool configured_dev[64] = {};
   int dev_ = 0;
   HIMO_CUDA_RET(cudaGetDevice(&dev_));
@@ -1233,7 +1245,6 @@ static int nsf_backward_hidden(const NsfBufs& b, const NsfAdamArgs& ad, float* d
   }
   k_nsf_dw<<<splits, kDwThreads, kDwTotal, stream>>>(maps, &b.ctl->stop, n_pad, k_split, splits, P, dW_part, b.small_part);
   HIMO_LAUNCH_RET();
-  k_nsf_small_final<<<kNsfLayers, 128, 0, stream>>>(b, splits); HIMO_LAUNCH_RET();
   return HIMO_OK;
 }
 
@@ -1252,7 +1263,7 @@ static int nsf_call_setup(void* workspace, size_t workspace_bytes, int n_max, in
   c->splits = ceil_div(n_pad, c->k_split);
   c->ad = c->L.ad;
   c->ad.params = c->b.params; c->ad.dW_part = c->L.dW_part; c->ad.splits = c->splits; c->ad.gb = c->b.gb;
-  c->ad.gW0 = c->b.gW0; c->ad.gb0 = c->b.gW0 + 384; c->ad.head_part = c->b.head_part; c->ad.head_blocks = c->head_blocks;
+  c->ad.gW0 = c->b.gW0; c->ad.gb0 = c->b.gW0 + 384; c->ad.small_part = c->b.small_part; c->ad.head_part = c->b.head_part; c->ad.head_blocks = c->head_blocks;
   c->ad.planes = planes; c->ad.lr = lr; c->ad.beta1 = 0.9f; c->ad.beta2 = 0.999f; c->ad.eps = 1e-8f;
   c->ad.inv_scale = 1.0f / c->b.grad_scale; c->ad.ctl = c->b.ctl;
   return HIMO_OK;
@@ -1341,7 +1352,7 @@ extern "C" int himo_nsf_optimize(const himo_nsf_desc* d, void* stream_) {
   const int splits = ceil_div(n_pad, k_split);
 
   NsfAdamArgs ad = L.ad;
-  ad.params = b.params; ad.dW_part = L.dW_part; ad.splits = splits; ad.gb = b.gb; ad.gW0 = b.gW0; ad.gb0 = b.gW0 + 384;
+  ad.params = b.params; ad.dW_part = L.dW_part; ad.splits = splits; ad.gb = b.gb; ad.gW0 = b.gW0; ad.gb0 = b.gW0 + 384; ad.small_part = b.small_part;
   ad.head_part = b.head_part; ad.head_blocks = head_blocks; ad.planes = P;
   ad.lr = d->lr; ad.beta1 = 0.9f; ad.beta2 = 0.999f; ad.eps = 1e-8f; ad.inv_scale = 1.0f / b.grad_scale; ad.ctl = b.ctl;
 
