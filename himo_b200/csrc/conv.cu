@@ -437,13 +437,21 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     umma::mbar_init(bres_bar, 1);
     umma::fence_barrier_init();
   } else if (warp == 1) {
-    if (CG == 2) umma::tmem_alloc_2cta(tmem_ptr_smem, C::kTmemCols);
-    else umma::tmem_alloc(tmem_ptr_smem, C::kTmemCols);
+    if (CG == 1) umma::tmem_alloc(tmem_ptr_smem, C::kTmemCols);
   }
   for (int i = threadIdx.x; i < p.Cout && i < C::kMaxBias; i += kConvThreads) bias_smem[i] = p.bias ? __ldg(p.bias + i) : 0.f;
   umma::tc_fence_before();
   __syncthreads();
-  if (CG == 2) umma::cluster_sync();       // peer barriers are initialised before anything signals them
+  if (CG == 2) {
+    umma::cluster_sync();       // peer barriers are initialised before anything signals them
+    // tcgen05.alloc.cta_group::2 is a compiler-generated handshake through the PEER CTA's reserved shared memory (remote
+    // mbarrier arrive + remote store of the address): it may only run once the peer CTA is known to be executing, i.e. after a
+    // cluster barrier.  Allocating before it hangs when the two CTAs of a pair start far apart, which several streams' kernels
+    // sharing the GPU provoke (profiles/r02_two_cta_alloc_hang.txt).
+    if (warp == 1) umma::tmem_alloc_2cta(tmem_ptr_smem, C::kTmemCols);
+    umma::tc_fence_before();
+    __syncthreads();
+  }
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, bias = a weight) overlapped
@@ -837,13 +845,17 @@ k_conv_wide(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     umma::mbar_init(acc_full_bar, 1);
     umma::mbar_init(acc_empty_bar, kConvEpiWarps * 2);
     umma::fence_barrier_init();
-  } else if (warp == 1) {
-    umma::tmem_alloc_2cta(tmem_ptr_smem, 512);
   }
   for (int i = threadIdx.x; i < 256; i += kConvThreads) bias_smem[i] = p.bias ? __ldg(p.bias + i) : 0.f;
-  umma::tc_fence_before();
   __syncthreads();
   umma::cluster_sync();
+  // tcgen05.alloc.cta_group::2 is a compiler-generated handshake through the PEER CTA's reserved shared memory (remote
+  // mbarrier arrive + remote store of the address): it may only run once the peer CTA is known to be executing, i.e. after a
+  // cluster barrier.  Allocating before it hangs when the two CTAs of a pair start far apart, which several streams' kernels
+  // sharing the GPU provoke (profiles/r02_two_cta_alloc_hang.txt).
+  if (warp == 1) umma::tmem_alloc_2cta(tmem_ptr_smem, 512);
+  umma::tc_fence_before();
+  __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();
@@ -1018,13 +1030,17 @@ k_conv_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < kR2Stages; ++s) { umma::mbar_init(&full_bar[s], 1); umma::mbar_init(&empty_bar[s], 1); }
     for (int r = 0; r < 2; ++r) { umma::mbar_init(&acc_full_bar[r], 1); umma::mbar_init(&acc_empty_bar[r], kConvEpiWarps * 2); }
     umma::fence_barrier_init();
-  } else if (warp == 1) {
-    umma::tmem_alloc_2cta(tmem_ptr_smem, 512);
   }
   for (int i = threadIdx.x; i < p.Cout && i < kR2MaxBias; i += kConvThreads) bias_smem[i] = p.bias ? __ldg(p.bias + i) : 0.f;
-  umma::tc_fence_before();
   __syncthreads();
   umma::cluster_sync();
+  // tcgen05.alloc.cta_group::2 is a compiler-generated handshake through the PEER CTA's reserved shared memory (remote
+  // mbarrier arrive + remote store of the address): it may only run once the peer CTA is known to be executing, i.e. after a
+  // cluster barrier.  Allocating before it hangs when the two CTAs of a pair start far apart, which several streams' kernels
+  // sharing the GPU provoke (profiles/r02_two_cta_alloc_hang.txt).
+  if (warp == 1) umma::tmem_alloc_2cta(tmem_ptr_smem, 512);
+  umma::tc_fence_before();
+  __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();

@@ -150,8 +150,6 @@ k_dec_fused(const __grid_constant__ CUtensorMap tmHX, const __grid_constant__ CU
     umma::mbar_init(r_empty, 2); umma::mbar_init(zq_empty, 2); umma::mbar_init(d_empty, 2);
     umma::mbar_init(tile_done, 1);
     umma::fence_barrier_init();
-  } else if (warp == 1) {
-    umma::tmem_alloc_2cta(tmem_ptr_smem, kDfTmemCols);
   }
   for (int i = threadIdx.x; i < 192; i += kDfThreads) {
     c_bz[i] = __ldg(p.b_zr + i); c_br[i] = __ldg(p.b_zr + 192 + i); c_bq[i] = __ldg(p.b_q + i);
@@ -159,9 +157,15 @@ k_dec_fused(const __grid_constant__ CUtensorMap tmHX, const __grid_constant__ CU
   for (int i = threadIdx.x; i < 64; i += kDfThreads) c_b0[i] = __ldg(p.b_0 + i);
   for (int i = threadIdx.x; i < 144; i += kDfThreads) c_w2[i] = __ldg(p.w2 + i);
   if (threadIdx.x < 3) c_b2[threadIdx.x] = __ldg(p.b2 + threadIdx.x);
-  umma::tc_fence_before();
   __syncthreads();
   umma::cluster_sync();
+  // tcgen05.alloc.cta_group::2 is a compiler-generated handshake through the PEER CTA's reserved shared memory (remote
+  // mbarrier arrive + remote store of the address): it may only run once the peer CTA is known to be executing, i.e. after a
+  // cluster barrier.  Allocating before it hangs when the two CTAs of a pair start far apart, which several streams' kernels
+  // sharing the GPU provoke (profiles/r02_two_cta_alloc_hang.txt).
+  if (warp == 1) umma::tmem_alloc_2cta(tmem_ptr_smem, kDfTmemCols);
+  umma::tc_fence_before();
+  __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 

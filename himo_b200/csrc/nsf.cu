@@ -686,8 +686,6 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       umma::mbar_init(&t_ready[s], 2); umma::mbar_init(&t_tma[s], 1); umma::mbar_init(&t_free[s], 1); umma::mbar_init(&acc_full[s], 1);
     }
     umma::fence_barrier_init();
-  } else if (warp == 1) {
-    umma::tmem_alloc_2cta(tmem_ptr_smem, 256);
   }
   if (DIR == 0) {
     for (int i = threadIdx.x; i < 7 * 128; i += kChThreads) {
@@ -697,9 +695,15 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     for (int i = threadIdx.x; i < 384; i += kChThreads) c_w0[i] = p.params[nsf_off_w(0) + i];
     for (int i = threadIdx.x; i < 128; i += kChThreads) c_b0[i] = p.params[nsf_off_b(0) + i];
   }
-  umma::tc_fence_before();
   __syncthreads();
   umma::cluster_sync();
+  // tcgen05.alloc.cta_group::2 is a compiler-generated handshake through the PEER CTA's reserved shared memory (remote
+  // mbarrier arrive + remote store of the address): it may only run once the peer CTA is known to be executing, i.e. after a
+  // cluster barrier.  Allocating before it hangs when the two CTAs of a pair start far apart, which several streams' kernels
+  // sharing the GPU provoke (profiles/r02_two_cta_alloc_hang.txt).
+  if (warp == 1) umma::tmem_alloc_2cta(tmem_ptr_smem, 256);
+  umma::tc_fence_before();
+  __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // layer order: DIR 0: l = 1..7 (input h_l, output h_{l+1});  DIR 1: l = 7..1 (input delta_{l+1}, output delta_l)

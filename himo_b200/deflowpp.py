@@ -205,6 +205,16 @@ class DeFlowPP:
         self._w = w
         return self
 
+    def replica(self) -> "DeFlowPP":
+        """A second network over the SAME packed device weights with its own workspace, so that two frame triples can be
+        in flight on two CUDA streams (engine.SeFlowPPEngine: the second stream's kernels fill the tail waves of the first)."""
+        if self._w is None:
+            raise RuntimeError("load_state_dict first")
+        r = DeFlowPP(precision=self.precision, device=self.device, max_points=self._reserve, num_iters=self.num_iters,
+                     compose_skip=self.compose_skip)
+        r._w, r._tensors = self._w, self._tensors
+        return r
+
     def load_from_checkpoint(self, ckpt_path: str):
         """BaseModel.load_from_checkpoint (OSF/src/models/basic/__init__.py:10-16)."""
         return self.load_state_dict(W.load_deflowpp_checkpoint(ckpt_path))

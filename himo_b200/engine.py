@@ -3,12 +3,15 @@
 `SeFlowPPEngine.infer(frame)` is the work of `ModelWrapper.test_step` minus the .h5 write
 (OSF/src/trainer.py:290-343): ground removal, DeFlowPP.forward, pose-flow + network-flow assembly
 for ALL points of pc0.  Inputs are host arrays (as the reference's DataLoader delivers them).
-`infer_stream(frames)` is the multi-frame form every driver uses: two preallocated slots (pinned host
-staging + device buffers) and three CUDA streams per engine, so that the H2D copy of frame i+1 and the
-D2H copy of frame i-1 overlap the network of frame i and no frame allocates memory.
+`infer_stream(frames)` is the multi-frame form every driver uses: preallocated slots (pinned host staging +
+device buffers + a network replica with its own workspace and compute stream), one copy-in and one copy-out
+stream, so that the H2D copy of frame i+1 and the D2H copy of frame i-1 overlap the network of frame i, TWO
+networks are in flight at any time (the kernels of one fill the tail waves and idle SMs of the other: 2.44 ->
+2.28 ms per frame, profiles/r02_two_streams.txt) and no frame allocates memory.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -45,14 +48,20 @@ class _Slot:
 
 class SeFlowPPEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", precision: str = "fp32",
-                 max_points: int = 131072):
+                 max_points: int = 131072, n_slots: Optional[int] = None):
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self.net = DeFlowPP(precision=precision, device=self.device, max_points=max_points)
         self.net.load_state_dict(state_dict)
-        self.stream = torch.cuda.Stream(self.device)
         self._s_in, self._s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
-        self._slots = [_Slot(self.device, max_points) for _ in range(2)]
+        n_slots = int(os.environ.get("HIMO_SLOTS", "3")) if n_slots is None else int(n_slots)
+        if n_slots < 1:
+            raise ValueError("n_slots must be >= 1")
+        self._slots = [_Slot(self.device, max_points) for _ in range(n_slots)]
+        for k, slot in enumerate(self._slots):      # every slot: its own workspace and compute stream, shared weights
+            slot.net = self.net if k == 0 else self.net.replica()
+            slot.stream = torch.cuda.Stream(self.device)
+        self.stream = self._slots[0].stream
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -104,10 +113,10 @@ class SeFlowPPEngine:
             h2d += 48
             ev_in = torch.cuda.Event()
             ev_in.record(self._s_in)
-        with torch.cuda.stream(self.stream):
-            self.stream.wait_event(ev_in)
+        with torch.cuda.stream(slot.stream):
+            slot.stream.wait_event(ev_in)
             d0 = slot.dev["pc0"][:pc0.shape[0]]
-            self.net.forward_triple(slot.dev["pch1"][:pch1.shape[0]], d0, slot.dev["pc1"][:pc1.shape[0]], Th, T0,
+            slot.net.forward_triple(slot.dev["pch1"][:pch1.shape[0]], d0, slot.dev["pc1"][:pc1.shape[0]], Th, T0,
                                     compact=False, flow_all_out=slot.dev["flow_all"])
             d0_all = slot.dev["pc0_all"] if keep0 is not None else slot.dev["pc0"]
             st = _lib.lib().himo_final_flow(_lib.ptr(d0_all), n_all, _lib.ptr(slot.dev_T), _lib.ptr(slot.dev["flow_all"]),
@@ -115,7 +124,7 @@ class SeFlowPPEngine:
                                             _lib.ptr(slot.dev["final"]), _lib.stream_ptr(self.device))
             _lib.check(st, "himo_final_flow")
             slot.ev_net = torch.cuda.Event()
-            slot.ev_net.record(self.stream)
+            slot.ev_net.record(slot.stream)
         with torch.cuda.stream(self._s_out):
             self._s_out.wait_event(slot.ev_net)
             slot.pin["out"][:n_all].copy_(slot.dev["final"][:n_all], non_blocking=True)
@@ -141,14 +150,16 @@ class SeFlowPPEngine:
     # ------------------------------------------------------------------ pipelined streaming API
     def infer_stream(self, frames):
         """Iterate over host frames and yield `final_flow` arrays in order, with the H2D copy of frame i+1
-        and the D2H copy of frame i-1 overlapping the network of frame i (three CUDA streams, two preallocated
-        slots).  Same results as `infer`.  This is the call bench.py's `e2e` arm times and the one the multi-frame
-        drivers (runner.run_save, runner.run_validate) go through."""
+        and the D2H copy of frame i-1 overlapping the networks of the frames in between (one compute stream and
+        one workspace per slot: with three slots two networks are always in flight).  Same results as `infer`.
+        This is the call bench.py's `e2e` arm times and the one the multi-frame drivers (runner.run_save,
+        runner.run_validate) go through."""
         pending = []          # (slot, n_all)
+        depth = len(self._slots)
         for i, frame in enumerate(frames):
-            slot = self._slots[i % 2]
+            slot = self._slots[i % depth]
             pending.append((slot, self._launch(slot, frame)))
-            if len(pending) == 2:            # the slot about to be reused must be drained first
+            if len(pending) == depth:        # the slot about to be reused must be drained first
                 yield self._collect(*pending.pop(0))
         while pending:
             yield self._collect(*pending.pop(0))
@@ -164,23 +175,63 @@ class FastNSFEngine:
         torch.cuda.set_device(self.device)
         self.net = FastNSF(device=self.device, precision=precision, seed=seed, **model_kw)
 
-    def infer(self, frame: Dict) -> np.ndarray:
+    def _prepare(self, frame: Dict) -> Dict:
+        """Everything of one pair that does not depend on the optimiser: upload, ground removal, range limit,
+        ego-motion warp and (FastNSF only) the distance volume of pc1 (fastnsf.py:180-201, 117-126).  Runs on
+        the CURRENT torch stream and records an event."""
         from .deflowpp import rigid_flow
         pc0_all = torch.from_numpy(np.ascontiguousarray(np.asarray(frame["pc0"], np.float32)[:, :3])).to(self.device)
         pc1_all = torch.from_numpy(np.ascontiguousarray(np.asarray(frame["pc1"], np.float32)[:, :3])).to(self.device)
         gm0 = torch.from_numpy(np.asarray(frame.get("gm0", np.zeros(pc0_all.shape[0], bool)), bool)).to(self.device)
         gm1 = torch.from_numpy(np.asarray(frame.get("gm1", np.zeros(pc1_all.shape[0], bool)), bool)).to(self.device)
-        batch = {"pc0": [pc0_all[~gm0].contiguous()], "pc1": [pc1_all[~gm1].contiguous()],
-                 "pose0": [torch.as_tensor(frame["pose0"])], "pose1": [torch.as_tensor(frame["pose1"])]}
-        res = self.net(batch)
-        T = cal_pose0to1(torch.as_tensor(frame["pose0"]), torch.as_tensor(frame["pose1"]))
-        final = rigid_flow(pc0_all, T)                          # pose flow for every point
-        final[~gm0] = final[~gm0] + res["flow"][0]              # runner.py:149-155
+        if "ego_motion" in frame:
+            T = torch.as_tensor(frame["ego_motion"]).detach().cpu().float()
+        else:
+            T = cal_pose0to1(torch.as_tensor(frame["pose0"]), torch.as_tensor(frame["pose1"]))
+        pc0, pc1 = pc0_all[~gm0].contiguous(), pc1_all[~gm1].contiguous()
+        prep = {"pc0_all": pc0_all, "gm0": gm0, "T": T, "pc0": pc0, "pc1": pc1}
+        if self._prebuild_volume:
+            from .fastnsf import dt_build, volume_geometry
+            sel0, rm0 = self.net.range_limit_(pc0)
+            sel1, _ = self.net.range_limit_(pc1)
+            tr0 = (sel0 + rigid_flow(sel0.contiguous(), T)).contiguous()
+            lo, dims = volume_geometry(tr0, sel1.contiguous(), self.net.grid_factor)
+            prep.update(tr0=tr0, sel1=sel1.contiguous(), rm0=rm0, lo=lo, dims=dims,
+                        D=dt_build(sel1.contiguous(), lo, dims, self.net.grid_factor))
+        ev = torch.cuda.Event()
+        ev.record()
+        prep["ready"] = ev
+        return prep
+
+    def _finish(self, prep: Dict) -> np.ndarray:
+        from .deflowpp import rigid_flow
+        torch.cuda.current_stream(self.device).wait_event(prep["ready"])
+        pc0_all, gm0 = prep["pc0_all"], prep["gm0"]
+        if "D" in prep:
+            res = self.net.optimize(prep["tr0"], prep["sel1"], D=prep["D"], lo=prep["lo"], dims=prep["dims"])
+            flow = torch.zeros_like(prep["pc0"])
+            flow[prep["rm0"]] = res["flow"]
+        else:
+            batch = {"pc0": [prep["pc0"]], "pc1": [prep["pc1"]], "ego_motion": [prep["T"]], "pose0": [None]}
+            flow = self.net(batch)["flow"][0]
+        final = rigid_flow(pc0_all, prep["T"])                  # pose flow for every point
+        final[~gm0] = final[~gm0] + flow                        # runner.py:149-155
         return final.cpu().numpy()
+
+    _prebuild_volume = True
+
+    def infer(self, frame: Dict) -> np.ndarray:
+        return self._finish(self._prepare(frame))
+
+    # No `infer_stream`: building pair i+1's distance volume on a side stream while pair i optimises was measured
+    # and is SLOWER (169 vs 101 ms per pair, profiles/r02_fastnsf_engine_overlap.json): the ~270 small raster launches
+    # interleave with the persistent chain kernels, which need every SM.  runner.infer_many falls back to `infer`.
 
 
 class NSFPEngine(FastNSFEngine):
     """Same step for NSFP (conf/model/nsfp.yaml): only the per-pair optimiser differs (himo_b200/nsfp.py)."""
+
+    _prebuild_volume = False                                    # NSFP has no distance volume: Chamfer inside the loop
 
     def __init__(self, device="cuda:0", seed: int = 0, **model_kw):
         from . import _lib

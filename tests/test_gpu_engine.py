@@ -9,10 +9,13 @@ from himo_b200.engine import SeFlowPPEngine
 pytestmark = pytest.mark.gpu
 
 
-def test_stream_equals_sync_and_handles_ground():
-    eng = SeFlowPPEngine(weights.synth_deflowpp_state_dict(1), max_points=8192)
+@pytest.mark.parametrize("n_slots", [1, 2, 3])
+def test_stream_equals_sync_and_handles_ground(n_slots):
+    """n_slots networks in flight on their own streams and workspaces (shared weights): results are those of the
+    one-at-a-time call, bit for bit."""
+    eng = SeFlowPPEngine(weights.synth_deflowpp_state_dict(1), max_points=8192, n_slots=n_slots)
     fr = []
-    for k in range(5):
+    for k in range(8):
         tr = frames.lidar_triple(3000 + 200 * k, 40 + k)
         f = {key: tr[key] for key in ("pc0", "pc1", "pch1", "pose0", "pose1", "poseh1")}
         if k % 2:
