@@ -62,6 +62,11 @@ class SeFlowPPEngine:
             slot.net = self.net if k == 0 else self.net.replica()
             slot.stream = torch.cuda.Stream(self.device)
         self.stream = self._slots[0].stream
+        if n_slots > 1 and os.environ.get("HIMO_PDL") is None:
+            # With several networks in flight the tail of every kernel is filled by another stream's CTAs; dependents
+            # launched early (programmatic dependent launch) would only hold SMs while they wait for their primary:
+            # 453-461 frames/s without it against 444-447 with it (profiles/r02_two_streams.txt).  Process-wide knob.
+            _lib.lib().himo_conv_set_pdl(0)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
