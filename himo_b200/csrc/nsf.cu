@@ -163,6 +163,181 @@ k_nsf_dt_pass(float* __restrict__ d, int n0, int n1, int n2, int axis, int dir, 
   }
 }
 
+// ------------------------------------------------------------------------------ DT: one cluster sweeps a whole pass
+// k_nsf_dt_sweep: the same recurrence as k_nsf_dt_pass for the two passes whose planes are small (axis 0 and 1: ~53 k cells
+// of the 1040 x 1030 x 52 volume), as ONE launch per (axis, direction) instead of 65.  A thread-block cluster owns the
+// plane: CTA r keeps rows [r R, (r+1) R) of the last three planes in shared memory, computes its rows of plane p from the
+// previous plane and sends its first / last row into the neighbours' halo rows with st.async (distributed shared memory),
+// which also signals the receiver's mbarrier for that plane.  There is no cluster barrier and no memory fence in the loop:
+// a step waits for its two halo rows (mbarrier) and for its own rows (__syncthreads).  Three state buffers make that safe: the
+// neighbour can run at most one step ahead (it needs my row of step s to start step s+1), and what it then writes is
+// generation s+2, a different buffer from the generation s that my slower warps may still be reading.
+// The old values of the next kDtcPF planes are prefetched with cp.async into a per-thread-private ring.
+// min / add with the same three constants in a different association: fminf is exact and x -> fl(x + c) is monotonic,
+// so min(fl(a+c), fl(b+c)) == fl(min(a,b) + c) and the result is bit-identical to k_nsf_dt_pass.
+constexpr int kDtcThreads = 1024;
+constexpr int kDtcPF = 4;
+constexpr int kDtcVS = 4;          // a thread owns a vertical strip of 4 cells: 18 shared-memory loads instead of 36
+constexpr int kDtcMaxStrips = 2;
+
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_f32(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(umma::smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kDtcThreads, 1)
+k_nsf_dt_sweep(float* __restrict__ d, int n0, int n1, int n2, int axis, int dir, float l00, float l01, float l11, int R,
+               int csize, long long* __restrict__ dbg) {
+  extern __shared__ float dtc_smem[];
+  __shared__ uint64_t halo_bar[3];
+  const int n[3] = {n0, n1, n2};
+  const long long stp = axis == 0 ? (long long)n1 * n2 : (long long)n2;       // stride of the sweep axis
+  const int sth = axis == 0 ? n2 : n1 * n2;                                   // stride of the in-plane row axis (y or x)
+  const int nh = axis == 0 ? n1 : n0, nw = n2, np = n[axis];
+  const int rank = (int)umma::cluster_ctarank();
+  const int row0 = rank * R;
+  // (written as comparisons of the inputs: nvcc 12.9 folds `max(0, min(R, x)) == R` into the predicate output of
+  //  VIMNMX.RELU and gets it wrong -- true for x <= R -- found with a device printf, profiles/r02_dt_cluster_sweep.txt)
+  const int left = nh - row0;
+  const int rows = left <= 0 ? 0 : (left < R ? left : R);
+  const bool talk_up = rank > 0 && left > 0;                   // rank-1 (always full then) and I exchange rows
+  const bool talk_down = rank + 1 < csize && left - R > 0;     // rank+1 has rows (then I am full)
+  const int SW = nw + 2, SB = (R + 2) * SW;                    // state row stride, state buffer size
+  float* ring = dtc_smem + 3 * (size_t)SB;                     // [kDtcPF][R * nw]
+  const int tid = threadIdx.x;
+  const int ngrp = (R + kDtcVS - 1) / kDtcVS;
+  int sbase[kDtcMaxStrips], gbase[kDtcMaxStrips], cbase[kDtcMaxStrips], nrow[kDtcMaxStrips];
+  uint32_t send_up = 0, send_dn = 0;                           // bit u*kDtcVS+j: that cell sits in my first / last row
+  int col1[kDtcMaxStrips];
+#pragma unroll
+  for (int u = 0; u < kDtcMaxStrips; ++u) {
+    const int strip = tid + u * kDtcThreads;
+    const int g = strip / nw, col = strip - g * nw;
+    const int rb = g * kDtcVS;
+    sbase[u] = (rb + 1) * SW + col + 1;
+    gbase[u] = (row0 + rb) * sth + col;
+    cbase[u] = rb * nw + col;
+    const int nr = g < ngrp ? rows - rb : 0;
+    nrow[u] = nr <= 0 ? 0 : (nr < kDtcVS ? nr : kDtcVS);
+    col1[u] = col + 1;
+    if (nrow[u] > 0 && rb == 0 && talk_up) send_up |= 1u << (u * kDtcVS);
+    if (nrow[u] > 0 && talk_down && rb <= R - 1 && R - 1 < rb + kDtcVS) send_dn |= 1u << (u * kDtcVS + R - 1 - rb);
+  }
+  for (int i = tid; i < 3 * SB; i += kDtcThreads) dtc_smem[i] = INFINITY;
+  if (tid == 0) {
+    for (int b = 0; b < 3; ++b) umma::mbar_init(&halo_bar[b], 1);
+    umma::fence_barrier_init();
+  }
+  __syncthreads();
+  umma::cluster_sync();                 // every CTA runs, has cleared its buffers and initialised its barriers
+  const uint32_t s_base = umma::smem_u32(dtc_smem), bar_base = umma::smem_u32(&halo_bar[0]);
+  const uint32_t up_s = talk_up ? umma::mapa_u32(s_base, (uint32_t)(rank - 1)) : 0u;
+  const uint32_t up_b = talk_up ? umma::mapa_u32(bar_base, (uint32_t)(rank - 1)) : 0u;
+  const uint32_t dn_s = talk_down ? umma::mapa_u32(s_base, (uint32_t)(rank + 1)) : 0u;
+  const uint32_t dn_b = talk_down ? umma::mapa_u32(bar_base, (uint32_t)(rank + 1)) : 0u;
+  const uint32_t halo_bytes = (uint32_t)(((talk_up ? 1 : 0) + (talk_down ? 1 : 0)) * nw * 4);
+  // my first row -> row R+1 of rank-1, my last row -> row 0 of rank+1, in generation buffer `buf`
+  auto send = [&](int buf, int u, int j, float v) {
+    const uint32_t bit = 1u << (u * kDtcVS + j);
+    if (send_up & bit) st_async_f32(up_s + (uint32_t)((buf * SB + (R + 1) * SW + col1[u]) * 4), v, up_b + 8u * buf);
+    if (send_dn & bit) st_async_f32(dn_s + (uint32_t)((buf * SB + col1[u]) * 4), v, dn_b + 8u * buf);
+  };
+  const int count = np - 1;
+  const int p_begin = dir > 0 ? 1 : np - 2;
+  if (tid == 0) umma::mbar_arrive_expect_tx(&halo_bar[0], halo_bytes);
+  {
+    const float* src = d + (long long)(p_begin - dir) * stp;         // the plane that is already final: generation 0
+#pragma unroll
+    for (int u = 0; u < kDtcMaxStrips; ++u)
+#pragma unroll
+      for (int j = 0; j < kDtcVS; ++j)
+        if (j < nrow[u]) {
+          const float v = src[gbase[u] + j * sth];
+          dtc_smem[sbase[u] + j * SW] = v;
+          send(0, u, j, v);
+        }
+  }
+  auto prefetch = [&](int slot, int plane) {
+    const float* src = d + (long long)plane * stp;
+    float* dst = ring + (size_t)slot * R * nw;
+#pragma unroll
+    for (int u = 0; u < kDtcMaxStrips; ++u)
+#pragma unroll
+      for (int j = 0; j < kDtcVS; ++j)
+        if (j < nrow[u]) cp_async_f32(dst + cbase[u] + j * nw, src + gbase[u] + j * sth);
+  };
+#pragma unroll
+  for (int j = 0; j < kDtcPF; ++j) {
+    if (j < count) prefetch(j, p_begin + j * dir);
+    cp_async_commit();
+  }
+  __syncthreads();
+  int cur = 0;                                    // buffer of generation s
+  long long t_cp = 0, t_halo = 0, t_comp = 0, t_sync = 0, t0 = 0;
+  for (int s = 0; s < count; ++s) {
+    const int p = p_begin + s * dir;
+    const int slot = s % kDtcPF;
+    const int nxt = cur == 2 ? 0 : cur + 1;
+    if (tid == 0 && s + 1 < count) umma::mbar_arrive_expect_tx(&halo_bar[nxt], halo_bytes);
+    if (dbg) t0 = clock64();
+    cp_async_wait<kDtcPF - 1>();
+    if (dbg) { const long long t = clock64(); t_cp += t - t0; t0 = t; }
+    umma::mbar_wait(&halo_bar[cur], (uint32_t)((s / 3) & 1));        // the neighbours' rows of generation s are here
+    if (dbg) { const long long t = clock64(); t_halo += t - t0; t0 = t; }
+    const float* prev = dtc_smem + cur * SB;
+    float* out = dtc_smem + nxt * SB;
+    float* dst = d + (long long)p * stp;
+    const float* old = ring + (size_t)slot * R * nw;
+    const bool talk = s + 1 < count;              // nobody reads the halos of the last generation
+#pragma unroll
+    for (int u = 0; u < kDtcMaxStrips; ++u) {
+      if (nrow[u] > 0) {
+        const float* q = prev + sbase[u] - SW;      // row above the strip
+        float a[kDtcVS + 2], m[kDtcVS + 2];
+#pragma unroll
+        for (int i = 0; i < kDtcVS + 2; ++i) {
+          if (i <= nrow[u] + 1) {
+            a[i] = q[i * SW];
+            m[i] = fminf(q[i * SW - 1], q[i * SW + 1]);
+          } else {
+            a[i] = INFINITY; m[i] = INFINITY;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kDtcVS; ++j) {
+          if (j < nrow[u]) {
+            const float e = fminf(m[j + 1], fminf(a[j], a[j + 2]));
+            const float x = fminf(m[j], m[j + 2]);
+            float best = fminf(old[cbase[u] + j * nw], __fadd_rn(a[j + 1], l00));
+            best = fminf(best, fminf(__fadd_rn(e, l01), __fadd_rn(x, l11)));
+            out[sbase[u] + j * SW] = best;
+            if (talk) send(nxt, u, j, best);
+            dst[gbase[u] + j * sth] = best;
+          }
+        }
+      }
+    }
+    if (s + kDtcPF < count) prefetch(slot, p + kDtcPF * dir);
+    cp_async_commit();
+    if (dbg) { const long long t = clock64(); t_comp += t - t0; t0 = t; }
+    __syncthreads();                              // my rows of generation s+1 are complete; generation s is no longer read
+    if (dbg) { const long long t = clock64(); t_sync += t - t0; t0 = t; }
+    cur = nxt;
+  }
+  if (dbg && (tid & 255) == 0) {                   // four probes per CTA: cycles in each part of a step, summed over the pass
+    long long* o = dbg + ((size_t)rank * 4 + (tid >> 8)) * 4;
+    o[0] = t_cp; o[1] = t_halo; o[2] = t_comp; o[3] = t_sync;
+  }
+  umma::cluster_sync();                           // no CTA leaves while a neighbour may still address its shared memory
+}
+
 // ------------------------------------------------------------------------------ MLP pieces outside the GEMMs
 // Activations h_l and back-propagated deltas are kept ROW-MAJOR only ([points][128 features], split planes).  The
 // forward and dX GEMMs read them as K-major operands (K = features); the weight-gradient kernel k_nsf_dw reads the
@@ -1333,6 +1508,76 @@ extern "C" int himo_nsf_volume_geometry(const float* pc0, int n0, const float* p
   return HIMO_OK;
 }
 
+static int g_dt_cluster = 1;
+static long long* g_dt_dbg = nullptr;   // device buffer [16 CTAs][4 probes][4] or null
+extern "C" int himo_nsf_set_dt_debug_buffer(long long* p) { g_dt_dbg = p; return HIMO_OK; }
+extern "C" int himo_nsf_set_dt_cluster(int enable) { g_dt_cluster = enable ? 1 : 0; return HIMO_OK; }
+
+// One (axis, direction) pass as a single cluster launch; HIMO_ERR_UNSUPPORTED when the plane does not fit a cluster.
+static int dt_sweep_launch(float* D, const int* n, int axis, int dir, float l00, float l01, float l11, cudaStream_t stream) {
+  const int nh = axis == 0 ? n[1] : n[0], nw = n[2];
+  static int max_cluster[64] = {};                            // per device: 16 where allowed, else 8, -1 = none
+  int dev = 0;
+  HIMO_CUDA_RET(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return HIMO_ERR_UNSUPPORTED;
+  for (int C = max_cluster[dev] > 0 ? max_cluster[dev] : 16; C >= 8; C >>= 1) {
+    if (max_cluster[dev] < 0) break;
+    const int R = ceil_div(nh, C);
+    if ((long long)ceil_div(R, kDtcVS) * nw > (long long)kDtcMaxStrips * kDtcThreads) continue;
+    const size_t smem = (3 * (size_t)(R + 2) * (nw + 2) + (size_t)kDtcPF * R * nw) * sizeof(float);
+    if (smem > 200 * 1024) continue;
+    if (max_cluster[dev] == 0) {                              // first call on this device: what cluster size may launch?
+      HIMO_CUDA_RET(cudaFuncSetAttribute(k_nsf_dt_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      if (C > 8 && cudaFuncSetAttribute(k_nsf_dt_sweep, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        continue;
+      }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(C); cfg.blockDim = dim3(kDtcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (max_cluster[dev] == 0) {
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, k_nsf_dt_sweep, &cfg) != cudaSuccess || nclusters < 1) {
+        cudaGetLastError();
+        continue;
+      }
+      max_cluster[dev] = C;
+    }
+    HIMO_CUDA_RET(cudaLaunchKernelEx(&cfg, k_nsf_dt_sweep, D, n[0], n[1], n[2], axis, dir, l00, l01, l11, R, C, g_dt_dbg));
+    himo_count_launch_();
+    return HIMO_OK;
+  }
+  if (max_cluster[dev] == 0) max_cluster[dev] = -1;
+  return HIMO_ERR_UNSUPPORTED;
+}
+
+// One raster pass in place, either way (tests / debugging): sweep = 1 -> k_nsf_dt_sweep, 0 -> the tiled launches.
+extern "C" int himo_nsf_dt_pass(float* D, const int32_t* dims, float grid_factor, int axis, int dir, int sweep, void* stream_) {
+  if (!D || !dims || axis < 0 || axis > 2 || (dir != 1 && dir != -1)) return HIMO_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const float sp = 1.0f / grid_factor;
+  const float l00 = sqrtf(sp * sp), l01 = sqrtf(sp * sp + sp * sp), l11 = sqrtf(sp * sp + sp * sp + sp * sp);
+  const int n[3] = {dims[0], dims[1], dims[2]};
+  if (n[axis] < 2) return HIMO_OK;
+  if (sweep) return axis < 2 ? dt_sweep_launch(D, n, axis, dir, l00, l01, l11, stream) : HIMO_ERR_UNSUPPORTED;
+  const int h = axis == 0 ? 1 : 0, w = axis == 2 ? 1 : 2;
+  dim3 grid(ceil_div(n[w], kDtTile), ceil_div(n[h], kDtTile));
+  int p = dir > 0 ? 1 : n[axis] - 2;
+  int remaining = n[axis] - 1;
+  while (remaining > 0) {
+    const int cnt = remaining < kDtSteps ? remaining : kDtSteps;
+    k_nsf_dt_pass<<<grid, 256, 0, stream>>>(D, n[0], n[1], n[2], axis, dir, p, cnt, l00, l01, l11);
+    HIMO_LAUNCH_RET();
+    p += dir * cnt;
+    remaining -= cnt;
+  }
+  return HIMO_OK;
+}
+
 // D[H][W][D] = FastGeodis-style raster Euclidean distance transform of the occupancy of pc1.
 extern "C" int himo_nsf_dt_build(const float* pc1, int n1, const float* lo, const int32_t* dims, float grid_factor,
                                  float* D, void* stream_) {
@@ -1351,6 +1596,11 @@ extern "C" int himo_nsf_dt_build(const float* pc1, int n1, const float* lo, cons
     const int h = axis == 0 ? 1 : 0, w = axis == 2 ? 1 : 2;
     dim3 grid(ceil_div(n[w], kDtTile), ceil_div(n[h], kDtTile));
     for (int dir = 1; dir >= -1; dir -= 2) {
+      if (axis < 2 && n[axis] > 1 && g_dt_cluster) {          // small planes: one cluster sweeps the whole pass
+        const int st = dt_sweep_launch(D, n, axis, dir, l00, l01, l11, stream);
+        if (st == HIMO_OK) continue;
+        if (st != HIMO_ERR_UNSUPPORTED) return st;            // does not fit (huge planes): the tiled passes below
+      }
       int p = dir > 0 ? 1 : n[axis] - 2;
       int remaining = n[axis] - 1;
       while (remaining > 0) {

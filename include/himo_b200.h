@@ -364,6 +364,16 @@ size_t himo_nsf_workspace_bytes(int n_max, int planes);
 /* A/B knob: 0 runs the seven hidden layers of the prior as GEMM launches (7 forward + 7 backward per iteration) instead of
  * the two fused chain kernels (k_mlp_chain: a 256-point tile stays in shared memory across the layers; default 1). */
 int himo_nsf_set_fused(int enable);
+/* 1 (default): the axis-0 / axis-1 raster passes of himo_nsf_dt_build run as one thread-block-cluster launch each
+ * (k_nsf_dt_sweep: halo rows exchanged through distributed shared memory, one cluster barrier per plane); 0: the tiled
+ * multi-launch passes.  Bit-identical results. */
+int himo_nsf_set_dt_cluster(int enable);
+/* One raster pass of the distance transform in place on D[dims] (axis 0..2, dir +1 / -1); sweep = 1 runs it as the
+ * cluster kernel (axis 0 / 1 only; HIMO_ERR_UNSUPPORTED when the plane does not fit), 0 as the tiled launches.  For tests. */
+int himo_nsf_dt_pass(float* D, const int32_t* dims, float grid_factor, int axis, int dir, int sweep, void* stream);
+/* Profiling aid: device buffer of 16 x 4 x 4 int64 (or NULL).  When set, k_nsf_dt_sweep adds up the clock64 cycles its steps
+ * spend in (cp.async wait, halo mbarrier wait, compute, __syncthreads) for four probe threads of every CTA. */
+int himo_nsf_set_dt_debug_buffer(long long* device_buffer);
 int himo_nsf_volume_geometry(const float* pc0, int n0, const float* pc1, int n1, float grid_factor,
                              float* lo_host, int32_t* dims_host, void* workspace, void* stream);
 int himo_nsf_dt_build(const float* pc1, int n1, const float* lo, const int32_t* dims, float grid_factor,
