@@ -116,20 +116,24 @@ def fastnsf(dev, frame: Dict, bf16_tflops: float, iters: int = 48) -> Dict:
     # the same configured run through the runner's engine (save.py model=fastnsf): host frames in, host flow out,
     # a fresh seeded prior per pair (so the early stop lands at a different iteration for every pair)
     from himo_b200.engine import FastNSFEngine
-    eng = FastNSFEngine(device=dev, itr_num=5000, early_patience=10)
-    eng.infer(frame)                                                    # warm-up (allocator, workspace)
-    n_pairs = 6
-    t0 = time.perf_counter()
-    its = []
-    for _ in range(n_pairs):
-        eng.infer(frame)
-        its.append(int(eng.net.last_info["iterations"]))
-    torch.cuda.synchronize()
-    stream_s = (time.perf_counter() - t0) / n_pairs
+    n_pairs = 8
+    eng_out = {}
+    for tag, workers in (("engine", 1), ("engine_stream", None)):
+        eng = FastNSFEngine(device=dev, itr_num=5000, early_patience=10, n_workers=workers)
+        for _ in eng.infer_stream(frame for _ in range(eng.n_workers)):      # warm-up (allocator, workspaces)
+            pass
+        eng._frame_no = 0
+        t0 = time.perf_counter()
+        for _ in eng.infer_stream(frame for _ in range(n_pairs)):
+            pass
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / n_pairs
+        eng_out[tag] = {"pairs": n_pairs, "pairs_in_flight": eng.n_workers, "seconds_per_pair": sec, "pairs_per_s": 1.0 / sec,
+                        "iterations": list(eng.last_iterations)}
+        del eng
+    eng_out["note"] = "host buffers in/out, a fresh seeded prior per pair (so every pair stops at a different iteration)"
     return {"n_points": n, "ms_per_iter": ms_iter, "iterations_timed": int(res["iterations"]), "dt_build_ms": dt_ms,
-            "engine": {"pairs": n_pairs, "seconds_per_pair": stream_s, "pairs_per_s": 1.0 / stream_s,
-                              "iterations": its,
-                              "note": "host buffers in/out; ground removal skipped when the frame has no gm0"},
+            "engine": eng_out["engine"], "engine_stream": eng_out["engine_stream"], "engine_note": eng_out["note"],
             "dt_dims": list(dims), "algorithmic_tflops": flops_iter / (ms_iter * 1e-3) / 1e12,
             "frac_of_bf16_peak": flops_iter / (ms_iter * 1e-3) / 1e12 / bf16_tflops,
             "configured_run": {"iterations": int(r2["iterations"]), "seconds": pair_s, "pairs_per_s": 1.0 / pair_s,

@@ -174,11 +174,24 @@ class FastNSFEngine:
     """`InferenceRunner._process_step` for FastNSF (OSF/src/runner.py:130-155): ground removal, per-pair
     optimisation, final_flow = pose_flow everywhere + optimised flow on the non-ground points."""
 
-    def __init__(self, device="cuda:0", precision: str = "fp32", seed: int = 0, **model_kw):
+    def __init__(self, device="cuda:0", precision: str = "fp32", seed: int = 0, n_workers: Optional[int] = None,
+                 **model_kw):
         from .fastnsf import FastNSF
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
-        self.net = FastNSF(device=self.device, precision=precision, seed=seed, **model_kw)
+        self.seed = int(seed)
+        self._make_net = lambda: FastNSF(device=self.device, precision=precision, seed=seed, **model_kw)
+        self.net = self._make_net()
+        self.n_workers = int(os.environ.get("HIMO_NSF_WORKERS", "3")) if n_workers is None else int(n_workers)
+        self._lanes = None                      # [(optimiser, stream)] of infer_stream, built on first use
+        self._frame_no = 0
+        self.last_iterations = []
+
+    def _init_for(self, frame_no: int):
+        """The reference draws a fresh Neural_Prior per pair from the global RNG (fastnsf.py:108-115); here pair k of an
+        engine gets the seeded prior k, whichever worker optimises it."""
+        from . import weights as W
+        return W.synth_neural_prior_state_dict(self.seed * 1000003 + frame_no)
 
     def _prepare(self, frame: Dict) -> Dict:
         """Everything of one pair that does not depend on the optimiser: upload, ground removal, range limit,
@@ -197,7 +210,7 @@ class FastNSFEngine:
         prep = {"pc0_all": pc0_all, "gm0": gm0, "T": T, "pc0": pc0, "pc1": pc1}
         if self._prebuild_volume:
             from .fastnsf import dt_build, volume_geometry
-            sel0, rm0 = self.net.range_limit_(pc0)
+            sel0, rm0 = self.net.range_limit_(pc0)           # (stateless helpers of the optimiser object)
             sel1, _ = self.net.range_limit_(pc1)
             tr0 = (sel0 + rigid_flow(sel0.contiguous(), T)).contiguous()
             lo, dims = volume_geometry(tr0, sel1.contiguous(), self.net.grid_factor)
@@ -208,17 +221,19 @@ class FastNSFEngine:
         prep["ready"] = ev
         return prep
 
-    def _finish(self, prep: Dict) -> np.ndarray:
+    def _finish(self, prep: Dict, net=None, frame_no: Optional[int] = None) -> np.ndarray:
         from .deflowpp import rigid_flow
+        net = self.net if net is None else net
         torch.cuda.current_stream(self.device).wait_event(prep["ready"])
         pc0_all, gm0 = prep["pc0_all"], prep["gm0"]
         if "D" in prep:
-            res = self.net.optimize(prep["tr0"], prep["sel1"], D=prep["D"], lo=prep["lo"], dims=prep["dims"])
+            res = net.optimize(prep["tr0"], prep["sel1"], D=prep["D"], lo=prep["lo"], dims=prep["dims"],
+                               init_state_dict=None if frame_no is None else self._init_for(frame_no))
             flow = torch.zeros_like(prep["pc0"])
             flow[prep["rm0"]] = res["flow"]
         else:
             batch = {"pc0": [prep["pc0"]], "pc1": [prep["pc1"]], "ego_motion": [prep["T"]], "pose0": [None]}
-            flow = self.net(batch)["flow"][0]
+            flow = net(batch)["flow"][0]
         final = rigid_flow(pc0_all, prep["T"])                  # pose flow for every point
         final[~gm0] = final[~gm0] + flow                        # runner.py:149-155
         return final.cpu().numpy()
@@ -226,11 +241,51 @@ class FastNSFEngine:
     _prebuild_volume = True
 
     def infer(self, frame: Dict) -> np.ndarray:
-        return self._finish(self._prepare(frame))
+        no = self._frame_no
+        self._frame_no += 1
+        out = self._finish(self._prepare(frame), frame_no=no if self._prebuild_volume else None)
+        self.last_iterations = [int(self.net.last_info.get("iterations", 0))]
+        return out
 
-    # No `infer_stream`: building pair i+1's distance volume on a side stream while pair i optimises was measured
-    # and is SLOWER (169 vs 101 ms per pair, profiles/r02_fastnsf_engine_overlap.json): the ~270 small raster launches
-    # interleave with the persistent chain kernels, which need every SM.  runner.infer_many falls back to `infer`.
+    def infer_stream(self, frames):
+        """Several pairs in flight (BASELINE configs[2]: pairs resident per GPU): `n_workers` host threads, each with its own
+        optimiser object (workspace) and CUDA stream, take the pairs in order; results come back in order.  The
+        optimiser call blocks its thread on the device stop flag (ctypes releases the GIL), so the distance-volume
+        build of one pair, the iteration kernels of another and the host-side polling overlap.  Same results as
+        `infer`: the initial prior of pair k depends on k only."""
+        if self.n_workers <= 1 or not self._prebuild_volume:
+            for frame in frames:
+                yield self.infer(frame)
+            return
+        from concurrent.futures import ThreadPoolExecutor
+        if self._lanes is None:
+            self._lanes = [(self.net if k == 0 else self._make_net(), torch.cuda.Stream(self.device))
+                           for k in range(self.n_workers)]
+        free = list(range(self.n_workers))
+
+        def work(lane, frame, no):
+            net, stream = self._lanes[lane]
+            torch.cuda.set_device(self.device)
+            with torch.cuda.stream(stream):
+                out = self._finish(self._prepare(frame), net=net, frame_no=no)
+            return lane, out, int(net.last_info.get("iterations", 0))
+
+        pending = []
+        self.last_iterations = []
+        with ThreadPoolExecutor(self.n_workers) as pool:
+            for frame in frames:
+                if not free:                                  # oldest first: results are yielded in order
+                    lane, out, its = pending.pop(0).result()
+                    free.append(lane)
+                    self.last_iterations.append(its)
+                    yield out
+                no = self._frame_no
+                self._frame_no += 1
+                pending.append(pool.submit(work, free.pop(0), frame, no))
+            while pending:
+                lane, out, its = pending.pop(0).result()
+                self.last_iterations.append(its)
+                yield out
 
 
 class NSFPEngine(FastNSFEngine):
@@ -246,3 +301,4 @@ class NSFPEngine(FastNSFEngine):
         torch.cuda.set_device(self.device)
         torch.manual_seed(seed)                                 # the networks are drawn from the global CPU RNG
         self.net = NSFP(**model_kw)
+        self.seed, self.n_workers, self._frame_no, self.last_iterations = int(seed), 1, 0, []

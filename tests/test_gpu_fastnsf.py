@@ -168,3 +168,26 @@ def test_dt_cluster_sweep_equals_tiled_passes(shape):
     assert torch.equal(D_sweep, D_tiled)
     lo_ref, hi_ref = fastnsf_ref.dt_bounds(pc0, pc, GF)
     assert torch.equal(D_sweep, fastnsf_ref.dt_build(pc, lo_ref, hi_ref, GF))
+
+
+def test_engine_pairs_in_flight_equal_one_at_a_time():
+    """FastNSFEngine.infer_stream: two worker threads, each with its own optimiser object and stream; pair k gets the
+    seeded prior k whichever worker runs it, so the results are those of the sequential `infer`."""
+    from himo_b200.engine import FastNSFEngine
+    rng = np.random.default_rng(5)
+    frames_ = []
+    for k in range(5):
+        n0, n1 = 5000 + 700 * k, 5200 - 300 * k
+        pc0 = (rng.random((n0, 3)).astype(np.float32) - 0.5) * np.array([60, 60, 4], np.float32)
+        pc1 = (rng.random((n1, 3)).astype(np.float32) - 0.5) * np.array([60, 60, 4], np.float32)
+        pose1 = np.eye(4); pose1[0, 3] = 0.3 * (k + 1)
+        frames_.append({"pc0": pc0, "pc1": pc1, "pose0": np.eye(4), "pose1": pose1,
+                        "gm0": pc0[:, 2] < -1.5, "gm1": pc1[:, 2] < -1.5})
+    a = FastNSFEngine(itr_num=12, early_patience=0, seed=3, n_workers=1)
+    b = FastNSFEngine(itr_num=12, early_patience=0, seed=3, n_workers=2)
+    one = [a.infer(f) for f in frames_]
+    many = list(b.infer_stream(iter(frames_)))
+    assert len(many) == 5 and b.last_iterations == [12] * 5
+    for x, y in zip(one, many):
+        assert x.shape == y.shape
+        np.testing.assert_array_equal(x, y)
