@@ -194,7 +194,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __global__ void __launch_bounds__(kDtcThreads, 1)
 k_nsf_dt_sweep(float* __restrict__ d, int n0, int n1, int n2, int axis, int dir, float l00, float l01, float l11, int R,
-               int csize, long long* __restrict__ dbg) {
+               int csize, int SW, long long* __restrict__ dbg) {
   extern __shared__ float dtc_smem[];
   __shared__ uint64_t halo_bar[3];
   const int n[3] = {n0, n1, n2};
@@ -209,7 +209,7 @@ k_nsf_dt_sweep(float* __restrict__ d, int n0, int n1, int n2, int axis, int dir,
   const int rows = left <= 0 ? 0 : (left < R ? left : R);
   const bool talk_up = rank > 0 && left > 0;                   // rank-1 (always full then) and I exchange rows
   const bool talk_down = rank + 1 < csize && left - R > 0;     // rank+1 has rows (then I am full)
-  const int SW = nw + 2, SB = (R + 2) * SW;                    // state row stride, state buffer size
+  const int SB = (R + 2) * SW;                                 // SW: state row stride (>= nw + 2, dt_sweep_row_stride), state buffer size
   float* ring = dtc_smem + 3 * (size_t)SB;                     // [kDtcPF][R * nw]
   const int tid = threadIdx.x;
   const int ngrp = (R + kDtcVS - 1) / kDtcVS;
@@ -268,10 +268,18 @@ k_nsf_dt_sweep(float* __restrict__ d, int n0, int n1, int n2, int axis, int dir,
     const float* src = d + (long long)plane * stp;
     float* dst = ring + (size_t)slot * R * nw;
 #pragma unroll
-    for (int u = 0; u < kDtcMaxStrips; ++u)
+    for (int u = 0; u < kDtcMaxStrips; ++u) {
+      if (nrow[u] == kDtcVS) {
+        float* r4 = dst + cbase[u];
+        const float* g4 = src + gbase[u];
 #pragma unroll
-      for (int j = 0; j < kDtcVS; ++j)
-        if (j < nrow[u]) cp_async_f32(dst + cbase[u] + j * nw, src + gbase[u] + j * sth);
+        for (int j = 0; j < kDtcVS; ++j) cp_async_f32(r4 + j * nw, g4 + j * sth);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kDtcVS; ++j)
+          if (j < nrow[u]) cp_async_f32(dst + cbase[u] + j * nw, src + gbase[u] + j * sth);
+      }
+    }
   };
 #pragma unroll
   for (int j = 0; j < kDtcPF; ++j) {
@@ -298,8 +306,32 @@ k_nsf_dt_sweep(float* __restrict__ d, int n0, int n1, int n2, int axis, int dir,
     const bool talk = s + 1 < count;              // nobody reads the halos of the last generation
 #pragma unroll
     for (int u = 0; u < kDtcMaxStrips; ++u) {
-      if (nrow[u] > 0) {
+      if (nrow[u] == kDtcVS) {                      // full strip: straight-line code, no per-cell predicates
         const float* q = prev + sbase[u] - SW;      // row above the strip
+        float a[kDtcVS + 2], m[kDtcVS + 2];
+#pragma unroll
+        for (int i = 0; i < kDtcVS + 2; ++i) {
+          a[i] = q[i * SW];
+          m[i] = fminf(q[i * SW - 1], q[i * SW + 1]);
+        }
+        const float* o4 = old + cbase[u];
+        float* w4 = out + sbase[u];
+        float* g4 = dst + gbase[u];
+        float best[kDtcVS];
+#pragma unroll
+        for (int j = 0; j < kDtcVS; ++j) {
+          const float e = fminf(m[j + 1], fminf(a[j], a[j + 2]));
+          const float x = fminf(m[j], m[j + 2]);
+          best[j] = fminf(fminf(o4[j * nw], __fadd_rn(a[j + 1], l00)), fminf(__fadd_rn(e, l01), __fadd_rn(x, l11)));
+          w4[j * SW] = best[j];
+          g4[j * sth] = best[j];
+        }
+        if (talk && ((send_up | send_dn) >> (u * kDtcVS) & 0xfu)) {
+#pragma unroll
+          for (int j = 0; j < kDtcVS; ++j) send(nxt, u, j, best[j]);
+        }
+      } else if (nrow[u] > 0) {                     // ragged last strip of a CTA
+        const float* q = prev + sbase[u] - SW;
         float a[kDtcVS + 2], m[kDtcVS + 2];
 #pragma unroll
         for (int i = 0; i < kDtcVS + 2; ++i) {
@@ -1513,6 +1545,15 @@ static long long* g_dt_dbg = nullptr;   // device buffer [16 CTAs][4 probes][4] 
 extern "C" int himo_nsf_set_dt_debug_buffer(long long* p) { g_dt_dbg = p; return HIMO_OK; }
 extern "C" int himo_nsf_set_dt_cluster(int enable) { g_dt_cluster = enable ? 1 : 0; return HIMO_OK; }
 
+// Row stride of the shared-memory state: a warp's 32 strips cover the tail of one 4-row group and the head of the next; with
+// 4 * SW == nw (mod 32) the head continues the bank sequence of the tail instead of colliding with it (ncu: 52 % of the
+// shared loads conflicted with SW = nw + 2 = 54).
+static int dt_sweep_row_stride(int nw) {
+  int sw = nw + 2;
+  if (nw % 4 == 0) while ((4 * sw - nw) % 32 != 0) ++sw;
+  return sw;
+}
+
 // One (axis, direction) pass as a single cluster launch; HIMO_ERR_UNSUPPORTED when the plane does not fit a cluster.
 static int dt_sweep_launch(float* D, const int* n, int axis, int dir, float l00, float l01, float l11, cudaStream_t stream) {
   const int nh = axis == 0 ? n[1] : n[0], nw = n[2];
@@ -1524,7 +1565,8 @@ static int dt_sweep_launch(float* D, const int* n, int axis, int dir, float l00,
     if (max_cluster[dev] < 0) break;
     const int R = ceil_div(nh, C);
     if ((long long)ceil_div(R, kDtcVS) * nw > (long long)kDtcMaxStrips * kDtcThreads) continue;
-    const size_t smem = (3 * (size_t)(R + 2) * (nw + 2) + (size_t)kDtcPF * R * nw) * sizeof(float);
+    const int SW = dt_sweep_row_stride(nw);
+    const size_t smem = (3 * (size_t)(R + 2) * SW + (size_t)kDtcPF * R * nw) * sizeof(float);
     if (smem > 200 * 1024) continue;
     if (max_cluster[dev] == 0) {                              // first call on this device: what cluster size may launch?
       HIMO_CUDA_RET(cudaFuncSetAttribute(k_nsf_dt_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1547,7 +1589,7 @@ static int dt_sweep_launch(float* D, const int* n, int axis, int dir, float l00,
       }
       max_cluster[dev] = C;
     }
-    HIMO_CUDA_RET(cudaLaunchKernelEx(&cfg, k_nsf_dt_sweep, D, n[0], n[1], n[2], axis, dir, l00, l01, l11, R, C, g_dt_dbg));
+    HIMO_CUDA_RET(cudaLaunchKernelEx(&cfg, k_nsf_dt_sweep, D, n[0], n[1], n[2], axis, dir, l00, l01, l11, R, C, SW, g_dt_dbg));
     himo_count_launch_();
     return HIMO_OK;
   }
