@@ -112,12 +112,14 @@ k_nsf_occupancy(const float* __restrict__ pc1, int n, NsfVol v, float* __restric
 // the update is an idempotent min over the same inputs this cannot change the result.
 constexpr int kDtSteps = 16;
 constexpr int kDtTile = 16;   // small tiles: the axis-0/1 planes are only ~50 k cells, 32x32 tiles left most SMs idle
-constexpr int kDtReg = kDtTile + 2 * kDtSteps;   // 48
+constexpr int kDtTileBig = 32;   // optional for planes of >= 256 k cells (himo_nsf_set_dt_big_tiles): 4x instead of 9x recomputation, but slower
 
+template <int kDtTile>
 __global__ void __launch_bounds__(256)
 k_nsf_dt_pass(float* __restrict__ d, int n0, int n1, int n2, int axis, int dir, int p_begin, int count,
               float l00, float l01, float l11) {
   // l00 = straight step, l01 = one lateral move, l11 = two lateral moves
+  constexpr int kDtReg = kDtTile + 2 * kDtSteps;   // 48 / 64
   __shared__ float buf[2][kDtReg][kDtReg + 1];
   const int n[3] = {n0, n1, n2};
   const long long st[3] = {(long long)n1 * n2, (long long)n2, 1};
@@ -1541,6 +1543,8 @@ extern "C" int himo_nsf_volume_geometry(const float* pc0, int n0, const float* p
 }
 
 static int g_dt_cluster = 1;
+static int g_dt_big_tiles = 0;   // measured: 32x32 tiles take 3.9 ms per axis-2 direction, 16x16 tiles 1.9 ms (profiles/r02_dt_cluster_sweep.txt)
+extern "C" int himo_nsf_set_dt_big_tiles(int enable) { g_dt_big_tiles = enable ? 1 : 0; return HIMO_OK; }
 static long long* g_dt_dbg = nullptr;   // device buffer [16 CTAs][4 probes][4] or null
 extern "C" int himo_nsf_set_dt_debug_buffer(long long* p) { g_dt_dbg = p; return HIMO_OK; }
 extern "C" int himo_nsf_set_dt_cluster(int enable) { g_dt_cluster = enable ? 1 : 0; return HIMO_OK; }
@@ -1597,6 +1601,25 @@ static int dt_sweep_launch(float* D, const int* n, int axis, int dir, float l00,
   return HIMO_ERR_UNSUPPORTED;
 }
 
+// One (axis, direction) pass as ceil((n_axis - 1) / 16) tiled launches; big planes (>= 256 k cells) take 32x32 tiles.
+static int dt_tiled_pass(float* D, const int* n, int axis, int dir, float l00, float l01, float l11, cudaStream_t stream) {
+  const int h = axis == 0 ? 1 : 0, w = axis == 2 ? 1 : 2;
+  const bool big = (long long)n[h] * n[w] >= (1 << 18) && g_dt_big_tiles;
+  const int tile = big ? kDtTileBig : kDtTile;
+  dim3 grid(ceil_div(n[w], tile), ceil_div(n[h], tile));
+  int p = dir > 0 ? 1 : n[axis] - 2;
+  int remaining = n[axis] - 1;
+  while (remaining > 0) {
+    const int cnt = remaining < kDtSteps ? remaining : kDtSteps;
+    if (big) k_nsf_dt_pass<kDtTileBig><<<grid, 256, 0, stream>>>(D, n[0], n[1], n[2], axis, dir, p, cnt, l00, l01, l11);
+    else k_nsf_dt_pass<kDtTile><<<grid, 256, 0, stream>>>(D, n[0], n[1], n[2], axis, dir, p, cnt, l00, l01, l11);
+    HIMO_LAUNCH_RET();
+    p += dir * cnt;
+    remaining -= cnt;
+  }
+  return HIMO_OK;
+}
+
 // One raster pass in place, either way (tests / debugging): sweep = 1 -> k_nsf_dt_sweep, 0 -> the tiled launches.
 extern "C" int himo_nsf_dt_pass(float* D, const int32_t* dims, float grid_factor, int axis, int dir, int sweep, void* stream_) {
   if (!D || !dims || axis < 0 || axis > 2 || (dir != 1 && dir != -1)) return HIMO_ERR_ARG;
@@ -1606,18 +1629,7 @@ extern "C" int himo_nsf_dt_pass(float* D, const int32_t* dims, float grid_factor
   const int n[3] = {dims[0], dims[1], dims[2]};
   if (n[axis] < 2) return HIMO_OK;
   if (sweep) return axis < 2 ? dt_sweep_launch(D, n, axis, dir, l00, l01, l11, stream) : HIMO_ERR_UNSUPPORTED;
-  const int h = axis == 0 ? 1 : 0, w = axis == 2 ? 1 : 2;
-  dim3 grid(ceil_div(n[w], kDtTile), ceil_div(n[h], kDtTile));
-  int p = dir > 0 ? 1 : n[axis] - 2;
-  int remaining = n[axis] - 1;
-  while (remaining > 0) {
-    const int cnt = remaining < kDtSteps ? remaining : kDtSteps;
-    k_nsf_dt_pass<<<grid, 256, 0, stream>>>(D, n[0], n[1], n[2], axis, dir, p, cnt, l00, l01, l11);
-    HIMO_LAUNCH_RET();
-    p += dir * cnt;
-    remaining -= cnt;
-  }
-  return HIMO_OK;
+  return dt_tiled_pass(D, n, axis, dir, l00, l01, l11, stream);
 }
 
 // D[H][W][D] = FastGeodis-style raster Euclidean distance transform of the occupancy of pc1.
@@ -1635,23 +1647,13 @@ extern "C" int himo_nsf_dt_build(const float* pc1, int n1, const float* lo, cons
   const float l00 = sqrtf(sp * sp), l01 = sqrtf(sp * sp + sp * sp), l11 = sqrtf(sp * sp + sp * sp + sp * sp);
   const int n[3] = {dims[0], dims[1], dims[2]};
   for (int axis = 0; axis < 3; ++axis) {
-    const int h = axis == 0 ? 1 : 0, w = axis == 2 ? 1 : 2;
-    dim3 grid(ceil_div(n[w], kDtTile), ceil_div(n[h], kDtTile));
     for (int dir = 1; dir >= -1; dir -= 2) {
       if (axis < 2 && n[axis] > 1 && g_dt_cluster) {          // small planes: one cluster sweeps the whole pass
         const int st = dt_sweep_launch(D, n, axis, dir, l00, l01, l11, stream);
         if (st == HIMO_OK) continue;
         if (st != HIMO_ERR_UNSUPPORTED) return st;            // does not fit (huge planes): the tiled passes below
       }
-      int p = dir > 0 ? 1 : n[axis] - 2;
-      int remaining = n[axis] - 1;
-      while (remaining > 0) {
-        const int cnt = remaining < kDtSteps ? remaining : kDtSteps;
-        k_nsf_dt_pass<<<grid, 256, 0, stream>>>(D, n[0], n[1], n[2], axis, dir, p, cnt, l00, l01, l11);
-        HIMO_LAUNCH_RET();
-        p += dir * cnt;
-        remaining -= cnt;
-      }
+      HIMO_RET(dt_tiled_pass(D, n, axis, dir, l00, l01, l11, stream));
     }
   }
   return HIMO_OK;
