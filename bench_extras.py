@@ -59,6 +59,12 @@ def knn(dev, clouds_100k, hbm_gbs: float, seed: int = 0) -> Dict:
         gbs = 20.0 * (a.shape[0] + b.shape[0]) / (ms * 1e-3) / 1e9
         out[tag] = {"n0": int(a.shape[0]), "n1": int(b.shape[0]), "ms": ms, "algorithmic_gbs": gbs,
                     "frac_of_hbm": gbs / hbm_gbs, "pairs_per_s": 1e3 / ms}
+        # radius sweep (BASELINE configs[4]): the radius-limited search the truncated losses / the nnd pass use
+        sweep = {}
+        for rad in (0.2, 0.5, 1.0, 2.0, 4.4):
+            ms_r = _time_ms(lambda: chamfer3d_ext.forward_radius(a, b, d0, d1, i0, i1, rad), max(3, reps // 2), warm=1)
+            sweep["%.1f m" % rad] = {"ms": ms_r, "matched_frac": float((i0 >= 0).float().mean().item())}
+        out[tag]["radius_sweep"] = sweep
     out["note"] = "exact search (indices bit-equal to the reference kernel); algorithmic bytes = 20*(N0+N1); launches are async, timed with CUDA events over back-to-back calls"
     return out
 

@@ -110,11 +110,11 @@ k_nsf_occupancy(const float* __restrict__ pc1, int n, NsfVol v, float* __restric
 // cells (the dependency cone widens by one cell per plane), so a pass costs n_axis/kDtSteps launches
 // instead of n_axis.  Halo cells may read a neighbour block's already-updated value of plane p; because
 // the update is an idempotent min over the same inputs this cannot change the result.
-constexpr int kDtSteps = 16;
+constexpr int kDtStepsDefault = 16;
 constexpr int kDtTile = 16;   // small tiles: the axis-0/1 planes are only ~50 k cells, 32x32 tiles left most SMs idle
 constexpr int kDtTileBig = 32;   // optional for planes of >= 256 k cells (himo_nsf_set_dt_big_tiles): 4x instead of 9x recomputation, but slower
 
-template <int kDtTile>
+template <int kDtTile, int kDtSteps>
 __global__ void __launch_bounds__(256)
 k_nsf_dt_pass(float* __restrict__ d, int n0, int n1, int n2, int axis, int dir, int p_begin, int count,
               float l00, float l01, float l11) {
@@ -1543,8 +1543,9 @@ extern "C" int himo_nsf_volume_geometry(const float* pc0, int n0, const float* p
 }
 
 static int g_dt_cluster = 1;
-static int g_dt_big_tiles = 0;   // measured: 32x32 tiles take 3.9 ms per axis-2 direction, 16x16 tiles 1.9 ms (profiles/r02_dt_cluster_sweep.txt)
-extern "C" int himo_nsf_set_dt_big_tiles(int enable) { g_dt_big_tiles = enable ? 1 : 0; return HIMO_OK; }
+static int g_dt_big_tiles = 3;   // variant of the tiled pass on planes of >= 256 k cells; per axis-2 direction at 1040 x 1030 x 52:
+                                 // 0 = 16x16 tiles x 16 planes 1.90 ms, 1 = 32x32 x 16: 3.87, 2 = 16x16 x 8: 1.41, 3 = 16x16 x 4: 1.28
+extern "C" int himo_nsf_set_dt_big_tiles(int variant) { g_dt_big_tiles = variant; return HIMO_OK; }
 static long long* g_dt_dbg = nullptr;   // device buffer [16 CTAs][4 probes][4] or null
 extern "C" int himo_nsf_set_dt_debug_buffer(long long* p) { g_dt_dbg = p; return HIMO_OK; }
 extern "C" int himo_nsf_set_dt_cluster(int enable) { g_dt_cluster = enable ? 1 : 0; return HIMO_OK; }
@@ -1601,18 +1602,23 @@ static int dt_sweep_launch(float* D, const int* n, int axis, int dir, float l00,
   return HIMO_ERR_UNSUPPORTED;
 }
 
-// One (axis, direction) pass as ceil((n_axis - 1) / 16) tiled launches; big planes (>= 256 k cells) take 32x32 tiles.
+// One (axis, direction) pass as tiled launches of 16 planes each; on big planes (the axis-2 pass: in-plane strides of 52 and
+// 53 560 floats, nothing coalesces) fewer planes per launch win: the halo cone and with it the recomputation shrink.
 static int dt_tiled_pass(float* D, const int* n, int axis, int dir, float l00, float l01, float l11, cudaStream_t stream) {
   const int h = axis == 0 ? 1 : 0, w = axis == 2 ? 1 : 2;
-  const bool big = (long long)n[h] * n[w] >= (1 << 18) && g_dt_big_tiles;
-  const int tile = big ? kDtTileBig : kDtTile;
+  // variant 0: 16x16 tiles, 16 planes per launch; 1: 32x32 tiles, 16 planes; 2: 16x16 tiles, 8 planes (halo 8: 4x recomputation)
+  const int variant = (long long)n[h] * n[w] >= (1 << 18) ? g_dt_big_tiles : 0;
+  const int tile = variant == 1 ? kDtTileBig : kDtTile;
+  const int steps = variant == 2 ? 8 : (variant == 3 ? 4 : kDtStepsDefault);
   dim3 grid(ceil_div(n[w], tile), ceil_div(n[h], tile));
   int p = dir > 0 ? 1 : n[axis] - 2;
   int remaining = n[axis] - 1;
   while (remaining > 0) {
-    const int cnt = remaining < kDtSteps ? remaining : kDtSteps;
-    if (big) k_nsf_dt_pass<kDtTileBig><<<grid, 256, 0, stream>>>(D, n[0], n[1], n[2], axis, dir, p, cnt, l00, l01, l11);
-    else k_nsf_dt_pass<kDtTile><<<grid, 256, 0, stream>>>(D, n[0], n[1], n[2], axis, dir, p, cnt, l00, l01, l11);
+    const int cnt = remaining < steps ? remaining : steps;
+    if (variant == 1) k_nsf_dt_pass<kDtTileBig, 16><<<grid, 256, 0, stream>>>(D, n[0], n[1], n[2], axis, dir, p, cnt, l00, l01, l11);
+    else if (variant == 2) k_nsf_dt_pass<kDtTile, 8><<<grid, 256, 0, stream>>>(D, n[0], n[1], n[2], axis, dir, p, cnt, l00, l01, l11);
+    else if (variant == 3) k_nsf_dt_pass<kDtTile, 4><<<grid, 256, 0, stream>>>(D, n[0], n[1], n[2], axis, dir, p, cnt, l00, l01, l11);
+    else k_nsf_dt_pass<kDtTile, 16><<<grid, 256, 0, stream>>>(D, n[0], n[1], n[2], axis, dir, p, cnt, l00, l01, l11);
     HIMO_LAUNCH_RET();
     p += dir * cnt;
     remaining -= cnt;

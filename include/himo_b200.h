@@ -368,9 +368,10 @@ int himo_nsf_set_fused(int enable);
  * (k_nsf_dt_sweep: halo rows exchanged through distributed shared memory, one cluster barrier per plane); 0: the tiled
  * multi-launch passes.  Bit-identical results. */
 int himo_nsf_set_dt_cluster(int enable);
-/* 1: the tiled raster passes use 32x32 tiles on planes of >= 256 k cells (the axis-2 pass); 0 (default): 16x16 everywhere
- * (measured faster: 1.9 vs 3.9 ms per direction at 1040 x 1030 x 52). */
-int himo_nsf_set_dt_big_tiles(int enable);
+/* Variant of the tiled raster pass on planes of >= 256 k cells (the axis-2 pass): 0 = 16x16 tiles advancing 16 planes per
+ * launch, 1 = 32x32 tiles x 16 planes, 2 = 16x16 x 8 planes, 3 (default) = 16x16 x 4 planes.  Bit-identical results;
+ * 1.90 / 3.87 / 1.41 / 1.28 ms per direction at 1040 x 1030 x 52. */
+int himo_nsf_set_dt_big_tiles(int variant);
 /* One raster pass of the distance transform in place on D[dims] (axis 0..2, dir +1 / -1); sweep = 1 runs it as the
  * cluster kernel (axis 0 / 1 only; HIMO_ERR_UNSUPPORTED when the plane does not fit), 0 as the tiled launches.  For tests. */
 int himo_nsf_dt_pass(float* D, const int32_t* dims, float grid_factor, int axis, int dir, int sweep, void* stream);

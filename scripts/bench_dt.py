@@ -24,7 +24,7 @@ for sweep in (0, 1):
             assert st == 0, st
             out[f"{'sweep' if sweep else 'tiled'}_axis{axis}_dir{dr}_ms"] = round(e0.elapsed_time(e1), 3)
     res[sweep] = D
-for big in (0, 1):
+for big in (0, 1, 2, 3):
     L.himo_nsf_set_dt_big_tiles(big)
     D = D0.clone()
     ts = []
@@ -34,9 +34,10 @@ for big in (0, 1):
         L.himo_nsf_dt_pass(_lib.ptr(D), dims_c, ctypes.c_float(10.0), 2, dr, 0, _lib.stream_ptr(D.device))
         e1.record(); torch.cuda.synchronize()
         ts.append(round(e0.elapsed_time(e1), 3))
-    out[f"axis2_tiles{32 if big else 16}_ms"] = ts
+    out[f"axis2_variant{big}_ms"] = ts
     res[10 + big] = D
-out["axis2_identical"] = bool(torch.equal(res[10], res[11]))
+out["axis2_identical"] = bool(torch.equal(res[10], res[11]) and torch.equal(res[10], res[12]) and torch.equal(res[10], res[13]))
+L.himo_nsf_set_dt_big_tiles(0)
 dbg = torch.zeros(16 * 4 * 4, dtype=torch.int64, device="cuda")
 L.himo_nsf_set_dt_debug_buffer.argtypes = [ctypes.c_void_p]
 L.himo_nsf_set_dt_debug_buffer(dbg.data_ptr())
