@@ -26,59 +26,56 @@ __device__ __forceinline__ void store_split8(__nv_bfloat16* dst, long long plane
   if (planes == 2) *(uint4*)(dst + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// one warp per point; each lane owns 8-channel chunks of the 288 = [before(96) | after(96) | offset feature(96)]
-// channels, so every global access is a 16/32-byte vector.
+// one thread per (point, 8-channel chunk) of the 288 = [before(96) | after(96) | offset feature(96)] channels: 36 chunks per
+// point, consecutive threads = consecutive chunks, so every global access is a 16/32-byte vector and all lanes work (with one
+// warp per point the second trip over the 36 chunks kept 4 of 32 lanes busy).
 __global__ void __launch_bounds__(256)
 k_dec_gather(DecGatherArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < a.n_pad; i += gridDim.x * wpb) {
+  const long long total = (long long)a.n_pad * 36;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / 36);
+    const int ch = (int)(t - (long long)i * 36);
     float4 p = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
     if (i < a.n) p = a.pt4[i];
     const int key = __float_as_int(p.w);
     float* h = a.h32 ? a.h32 + (size_t)i * 192 : nullptr;
     __nv_bfloat16* hx = a.hx_planes + (size_t)i * 288;
     __nv_bfloat16* rhx = a.rhx_planes ? a.rhx_planes + (size_t)i * 288 : nullptr;
-    // point_offsets = p - ((c * voxel_size + min) + voxel_size/2), every step rounded to fp32
-    // (DynamicVoxelizer._get_point_offsets, encoder.py:506-523)
-    float ox = 0.f, oy = 0.f, oz = 0.f;
+    const int c0 = ch * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (key >= 0) {
-      const int cy = key / a.gx, cx = key - cy * a.gx;
-      ox = p.x - __fadd_rn(__fadd_rn(__fmul_rn((float)cx, a.vx), a.x_min), a.hx);
-      oy = p.y - __fadd_rn(__fadd_rn(__fmul_rn((float)cy, a.vy), a.y_min), a.hy);
-      oz = p.z - __fadd_rn(__fadd_rn(__fmul_rn(0.f, a.vz), a.z_min), a.hz);
-    }
-    for (int ch = lane; ch < 36; ch += 32) {
-      const int c0 = ch * 8;
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (key >= 0) {
-        if (ch < 12) {
-          // before_pseudoimage[:, y, x]: the exact fp32 voxel feature of frame f, zero where that frame is empty
-          const int f = ch >> 2;
-          const unsigned* bm = a.bitmap + (size_t)f * a.n_words;
-          if ((__ldg(bm + (key >> 5)) >> (key & 31)) & 1u) {
-            const int r = bitmap_rank_lb(bm, a.word_prefix + (size_t)f * a.n_words, key);
-            const float4* src = (const float4*)(a.voxel_feats + ((size_t)f * a.n_max + r) * 32 + (ch & 3) * 8);
-            *(float4*)&v[0] = __ldg(src); *(float4*)&v[4] = __ldg(src + 1);
-          }
-        } else if (ch < 24) {
-          const float4* src = (const float4*)(a.after + (size_t)key * a.c_after + (c0 - 96));   // after[:, y, x]
+      if (ch < 12) {
+        // before_pseudoimage[:, y, x]: the exact fp32 voxel feature of frame f, zero where that frame is empty
+        const int f = ch >> 2;
+        const unsigned* bm = a.bitmap + (size_t)f * a.n_words;
+        if ((__ldg(bm + (key >> 5)) >> (key & 31)) & 1u) {
+          const int r = bitmap_rank_lb(bm, a.word_prefix + (size_t)f * a.n_words, key);
+          const float4* src = (const float4*)(a.voxel_feats + ((size_t)f * a.n_max + r) * 32 + (ch & 3) * 8);
           *(float4*)&v[0] = __ldg(src); *(float4*)&v[4] = __ldg(src + 1);
-        } else {
+        }
+      } else if (ch < 24) {
+        const float4* src = (const float4*)(a.after + (size_t)key * a.c_after + (c0 - 96));   // after[:, y, x]
+        *(float4*)&v[0] = __ldg(src); *(float4*)&v[4] = __ldg(src + 1);
+      } else {
+        // point_offsets = p - ((c * voxel_size + min) + voxel_size/2), every step rounded to fp32
+        // (DynamicVoxelizer._get_point_offsets, encoder.py:506-523)
+        const int cy = key / a.gx, cx = key - cy * a.gx;
+        const float ox = p.x - __fadd_rn(__fadd_rn(__fmul_rn((float)cx, a.vx), a.x_min), a.hx);
+        const float oy = p.y - __fadd_rn(__fadd_rn(__fmul_rn((float)cy, a.vy), a.y_min), a.hy);
+        const float oz = p.z - __fadd_rn(__fadd_rn(__fmul_rn(0.f, a.vz), a.z_min), a.hz);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int c = c0 - 192 + k;
-            float t = __ldg(a.w_off + c * 3) * ox;
-            t = fmaf(__ldg(a.w_off + c * 3 + 1), oy, t);
-            t = fmaf(__ldg(a.w_off + c * 3 + 2), oz, t);
-            v[k] = t + __ldg(a.b_off + c);
-          }
+        for (int k = 0; k < 8; ++k) {
+          const int c = c0 - 192 + k;
+          float tt = __ldg(a.w_off + c * 3) * ox;
+          tt = fmaf(__ldg(a.w_off + c * 3 + 1), oy, tt);
+          tt = fmaf(__ldg(a.w_off + c * 3 + 2), oz, tt);
+          v[k] = tt + __ldg(a.b_off + c);
         }
       }
-      if (h && ch < 24) { *(float4*)(h + c0) = *(float4*)&v[0]; *(float4*)(h + c0 + 4) = *(float4*)&v[4]; }
-      store_split8(hx + c0, a.plane_stride, a.planes, v);
-      if (rhx && ch >= 24) store_split8(rhx + c0, a.plane_stride, a.planes, v);
     }
+    if (h && ch < 24) { *(float4*)(h + c0) = *(float4*)&v[0]; *(float4*)(h + c0 + 4) = *(float4*)&v[4]; }
+    store_split8(hx + c0, a.plane_stride, a.planes, v);
+    if (rhx && ch >= 24) store_split8(rhx + c0, a.plane_stride, a.planes, v);
   }
 }
 
@@ -174,7 +171,7 @@ using namespace himo;
 namespace himo {
 
 int dec_gather(const DecGatherArgs& a, cudaStream_t stream) {
-  k_dec_gather<<<min(ceil_div(a.n_pad, 8), kNumSMs * 8), 256, 0, stream>>>(a);
+  k_dec_gather<<<(int)min(ceil_div_ll((long long)a.n_pad * 36, 256), (long long)kNumSMs * 16), 256, 0, stream>>>(a);
   HIMO_LAUNCH_RET();
   return HIMO_OK;
 }
