@@ -10,6 +10,7 @@
 // (dW, split-K) on the tcgen05 GEMM kernel of conv.cu with ReLU / ReLU-mask / transposed stores fused into
 // its epilogue; loss, best-flow snapshot, early stopping and Adam live in a device control block; the
 // host only polls a stop flag every few iterations.
+#include <cstdlib>
 #include <cudaTypedefs.h>
 #include <math.h>
 
@@ -1059,9 +1060,6 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           umma::mbar_wait(&acc_full[sl], nacc[sl] & 1);
           ++nacc[sl];
           umma::tc_fence_after();
-          // the store of THIS slot's previous layer (two groups ago) has read the tile; the other slot's may still be in flight
-          if (issuer) { if (nslot == 2) umma::tma_store_wait_read_but1(); else umma::tma_store_wait_read(); }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
           uint32_t mbits[2] = {0u, 0u};
           if (DIR == 1) {
             const uint2 mm = *(const uint2*)(p.mask[l] + grow * 4 + half * 2);
@@ -1070,7 +1068,12 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           uint32_t accs[4][16];                                   // all four loads in flight before ONE wait
 #pragma unroll
           for (int g = 0; g < 4; ++g) umma::tmem_ld_32x16(tlane + (uint32_t)(sl * 128 + half * 64 + g * 16), accs[g]);
+          // the store of THIS slot's previous layer (two groups ago) has read the tile; the other slot's may still be in flight.
+          // Waited for as late as possible -- the accumulator loads above are already on their way -- because the stores
+          // drain at the DRAM write rate and every microsecond of slack is a microsecond of overlap.
+          if (issuer) { if (nslot == 2) umma::tma_store_wait_read_but1(); else umma::tma_store_wait_read(); }
           umma::tmem_ld_wait();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = half * 64 + g * 16;
