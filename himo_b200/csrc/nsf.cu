@@ -828,7 +828,7 @@ k_nsf_dw(const __grid_constant__ DwMaps maps, const int* __restrict__ stop_flag,
 //   * DIR 1 (backward, dX): prologue = TMA load of delta_8; layers 7..1 with the transposed weights; epilogue = the ReLU
 //     mask read back from those bits (instead of re-reading the 50 MB activation tensor per layer).
 // One accumulator (hi*hi and cross terms together: chains are 24 MMAs), 128 TMEM columns.
-constexpr int kChThreads = 320;
+constexpr int kChThreads = 352;                       // TMA producer, MMA issuer, 8 epilogue warps, store warp
 constexpr int kChTile = 128 * 64;                      // one 32-channel plane tile of 128 rows: 8 KB
 constexpr int kChT = 4 * 2 * kChTile;                  // activation tile: 64 KB
 constexpr int kChSlots = 2;                            // two point tiles in flight per CTA: the epilogue of one overlaps the MMAs of the other
@@ -879,7 +879,9 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   uint64_t* t_tma = t_ready + 2;                          // [2] DIR 1: delta_8 landed (tx, both CTAs)
   uint64_t* t_free = t_tma + 2;                           // [2] DIR 1: this CTA's tile may be overwritten by the next TMA load
   uint64_t* acc_full = t_free + 2;                        // [2]
-  uint32_t* tmem_ptr_smem = (uint32_t*)(acc_full + 2);
+  uint64_t* st_req = acc_full + 2;                        // [2] slot's tile is complete: the store warp may send it to HBM
+  uint64_t* st_done = st_req + 2;                         // [2] that store has read the tile: it may be rewritten
+  uint32_t* tmem_ptr_smem = (uint32_t*)(st_done + 2);
   float* c_bias = (float*)(smem + kChOffConst);          // [7][128] biases of layers 1..7
   float* c_w0 = c_bias + 7 * 128;                         // [128][3]
   float* c_b0 = c_w0 + 384;                               // [128]
@@ -894,6 +896,7 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     for (int s = 0; s < kChWStages; ++s) { umma::mbar_init(&w_full[s], 1); umma::mbar_init(&w_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       umma::mbar_init(&t_ready[s], 2); umma::mbar_init(&t_tma[s], 1); umma::mbar_init(&t_free[s], 1); umma::mbar_init(&acc_full[s], 1);
+      umma::mbar_init(&st_req[s], 1); umma::mbar_init(&st_done[s], 1);
     }
     umma::fence_barrier_init();
   }
@@ -998,6 +1001,42 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         }
       }
     }
+  } else if (warp == 10) {
+    // ===================== store warp: the HBM copy of every finished tile =====================
+    // cp.async.bulk.tensor stores stall their thread while the SM's TMA queue is backed up behind DRAM.  Issued by an
+    // epilogue thread they held up the epilogue (and, before the ready signal was moved in front of them, the MMAs): every
+    // stored byte cost its DRAM write time on top of the compute.  Here they stall a warp that has nothing else to do.
+    uint32_t nst[2] = {0u, 0u};
+    auto store_tile = [&](const CUtensorMap* tm, int sl, int row0) {
+      umma::mbar_wait(&st_req[sl], nst[sl] & 1);
+      ++nst[sl];
+      uint8_t* sT = smem + sl * kChT;
+      if (umma::elect_one()) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) umma::tma_store_3d(tm, sT + (c * 2 + pl) * kChTile, c * 32, row0, pl);
+        umma::tma_store_commit();
+        umma::tma_store_wait_read();                       // (the elected lane owns the bulk groups)
+        umma::mbar_arrive(&st_done[sl]);
+      }
+      __syncwarp();
+    };
+    for (int u = worker; u < n_super; u += n_workers) {
+      const int nslot = (2 * u + 1 < p.n_pair_tiles) ? 2 : 1;
+      if (DIR == 0)
+        for (int sl = 0; sl < nslot; ++sl) store_tile(&maps.act[1], sl, ((2 * u + sl) * 2 + (int)cta_rank) * 128);
+      for (int k = 0; k < 7; ++k) {
+        const int l = DIR == 0 ? 1 + k : 7 - k;
+        for (int sl = 0; sl < nslot; ++sl) {
+          store_tile(&maps.act[DIR == 0 ? l + 1 : l], sl, ((2 * u + sl) * 2 + (int)cta_rank) * 128);
+          // DIR 1: the tiles may be reloaded with the next super-tile's delta_8 once their last stores have read them
+          if (DIR == 1 && k == 6 && sl == nslot - 1 && umma::elect_one())
+            for (int z = 0; z < nslot; ++z) umma::mbar_arrive(&t_free[z]);
+        }
+      }
+    }
+    if (umma::elect_one()) umma::tma_store_wait_all();       // same lane as every elect_one above: the warp is fully converged
   } else {
     // ===================== epilogue warps: layer-0 prologue (DIR 0), then one in-place epilogue per (layer, slot) =====================
     const int q = warp & 3, half = (warp - 2) >> 2, row = q * 32 + lane;
@@ -1005,26 +1044,27 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     const uint32_t a_t_ready0 = umma::mapa_u32(umma::smem_u32(&t_ready[0]), 0);
     const uint32_t a_t_ready1 = umma::mapa_u32(umma::smem_u32(&t_ready[1]), 0);
     const bool issuer = warp == 2 && lane == 0;
-    uint32_t nacc[2] = {0u, 0u};
-    auto publish = [&](const CUtensorMap* tm, uint8_t* sT, int row0) {      // tile complete in shared memory: release it to MMA / TMA
+    uint32_t nacc[2] = {0u, 0u}, nreq[2] = {0u, 0u};
+    // tile complete in shared memory: release it to the MMA warp (ready != 0: the leader's t_ready barrier) and to the
+    // store warp
+    auto publish = [&](int sl, uint32_t ready) {
       umma::tc_fence_before();
       umma::fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (issuer) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int pl = 0; pl < 2; ++pl) umma::tma_store_3d(tm, sT + (c * 2 + pl) * kChTile, c * 32, row0, pl);
-        umma::tma_store_commit();
+        if (ready) umma::mbar_arrive_cluster(ready);
+        umma::mbar_arrive(&st_req[sl]);
       }
+      ++nreq[sl];
     };
+    // before a slot's tile is rewritten: its previous store (if any) has read it
+    auto tile_writable = [&](int sl) { if (nreq[sl] > 0) umma::mbar_wait(&st_done[sl], (nreq[sl] - 1) & 1); };
     for (int u = worker; u < n_super; u += n_workers) {
       const int nslot = (2 * u + 1 < p.n_pair_tiles) ? 2 : 1;
       if (DIR == 0) {
         // ---- layer 0: h_1 = relu(W0 x + b0), 64 channels per thread, straight into the operand tiles
-        if (issuer) umma::tma_store_wait_read();                 // the previous super-tile's last stores have read the tiles
-        asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int sl = 0; sl < nslot; ++sl) {
+          tile_writable(sl);                                      // the previous super-tile's last store has read the tile
           uint8_t* sT = smem + sl * kChT;
           const int row0 = ((2 * u + sl) * 2 + (int)cta_rank) * 128;
           const long long grow = (long long)row0 + row;
@@ -1047,8 +1087,7 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             ch_store16(sT + (c * 2) * kChTile, sT + (c * 2 + 1) * kChTile, row, (g & 1) * 2, v);
           }
           *(uint2*)(p.mask[1] + grow * 4 + half * 2) = make_uint2(mbits[0], mbits[1]);
-          publish(&maps.act[1], sT, row0);
-          if (issuer) umma::mbar_arrive_cluster(sl ? a_t_ready1 : a_t_ready0);
+          publish(sl, sl ? a_t_ready1 : a_t_ready0);
         }
       }
       for (int k = 0; k < 7; ++k) {
@@ -1068,12 +1107,10 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           uint32_t accs[4][16];                                   // all four loads in flight before ONE wait
 #pragma unroll
           for (int g = 0; g < 4; ++g) umma::tmem_ld_32x16(tlane + (uint32_t)(sl * 128 + half * 64 + g * 16), accs[g]);
-          // the store of THIS slot's previous layer (two groups ago) has read the tile; the other slot's may still be in flight.
-          // Waited for as late as possible -- the accumulator loads above are already on their way -- because the stores
-          // drain at the DRAM write rate and every microsecond of slack is a microsecond of overlap.
-          if (issuer) { if (nslot == 2) umma::tma_store_wait_read_but1(); else umma::tma_store_wait_read(); }
+          // the store of THIS slot's previous layer has read the tile (waited for as late as possible: the accumulator
+          // loads above are already on their way)
+          tile_writable(sl);
           umma::tmem_ld_wait();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = half * 64 + g * 16;
@@ -1093,16 +1130,10 @@ k_mlp_chain(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             ch_store16(sT + (c * 2) * kChTile, sT + (c * 2 + 1) * kChTile, row, (g & 1) * 2, v);
           }
           if (DIR == 0 && l < 7) *(uint2*)(p.mask[l + 1] + grow * 4 + half * 2) = make_uint2(mbits[0], mbits[1]);
-          publish(&maps.act[DIR == 0 ? l + 1 : l], sT, row0);
-          if (k < 6) { if (issuer) umma::mbar_arrive_cluster(sl ? a_t_ready1 : a_t_ready0); }
-          else if (DIR == 1 && issuer) {
-            // the tile may be reloaded once its last store has read it (the other slot's final store, if any, is younger)
-            if (sl == nslot - 1) { umma::tma_store_wait_read(); for (int z = 0; z < nslot; ++z) umma::mbar_arrive(&t_free[z]); }
-          }
+          publish(sl, k < 6 ? (sl ? a_t_ready1 : a_t_ready0) : 0u);
         }
       }
     }
-    if (issuer) umma::tma_store_wait_all();
   }
   umma::tc_fence_before();
   __syncthreads();
