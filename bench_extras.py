@@ -117,6 +117,8 @@ def fastnsf(dev, frame: Dict, bf16_tflops: float, iters: int = 48) -> Dict:
     flops_iter = 0.692e6 * n                                            # 0.692 MFLOP per point per iteration
     # the configured run (patience 10, min_delta 5e-5, conf/model/fastnsf.yaml) on the same pair, DT build included
     net2 = F.FastNSF(itr_num=5000, early_patience=10, device=dev)
+    net2.optimize(tr0, sel1, init_state_dict=sd)                        # warm-up: workspace and volume blocks from the allocator
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     r2 = net2.optimize(tr0, sel1, init_state_dict=sd)
     torch.cuda.synchronize()
