@@ -603,6 +603,139 @@ k_nsf_head(NsfBufs b, const float* __restrict__ D, NsfVol vol) {
   head_backward(b, sW8, i, d0, d1, d2, val, red);
 }
 
+// The same head with a WARP per point instead of a thread per point (himo_nsf_set_head_warp, default): lanes own 4 features
+// each, so h_8 is read and delta_8 written as coalesced 256-byte rows (a thread per point walked its own 512 bytes: 32 lines
+// per load instruction), the three dot products are shuffle-reduced, and four points go through each stage together so that
+// the dependent global loads (h_8, then the eight distance-volume corners, fetched by eight lanes per point) are in flight
+// for four points at once.  Block = 128 points as before (same head_part layout); sums are taken in a fixed order.
+__global__ void __launch_bounds__(kHeadThreads)
+k_nsf_head_warp(NsfBufs b, const float* __restrict__ D, NsfVol vol) {
+  if (b.ctl->stop) return;
+  __shared__ float red[kHeadThreads / 32][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool split = b.planes == 2;
+  const unsigned FULL = 0xffffffffu;
+  float w[3][4];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[k][u] = __ldg(b.params + nsf_off_w(8) + k * 128 + lane * 4 + u);
+  const float b8x = __ldg(b.params + nsf_off_b(8)), b8y = __ldg(b.params + nsf_off_b(8) + 1), b8z = __ldg(b.params + nsf_off_b(8) + 2);
+  const float sN = b.grad_scale / (float)b.n;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const int base = blockIdx.x * kHeadThreads + warp * 32;
+  const int q = lane >> 3, corner = lane & 7;           // trilinear stage: 8 lanes per point, one corner each
+  for (int p0 = 0; p0 < 32; p0 += 4) {
+    const int i0 = base + p0;
+    if (i0 >= b.n_pad) break;                            // n_pad is a multiple of 256: groups of four are whole
+    // ---- h_8 rows of four points, 4 features per lane
+    float h[4][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const __nv_bfloat16* row = b.H[8] + (long long)(i0 + t) * 128 + lane * 4;
+      const uint2 a = *(const uint2*)row;
+      if (split) {
+        const uint2 l = *(const uint2*)(row + b.ps);
+        const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+        const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+        h[t][0] = h0.x + l0.x; h[t][1] = h0.y + l0.y; h[t][2] = h1.x + l1.x; h[t][3] = h1.y + l1.y;
+      } else {
+        h[t][0] = __uint_as_float(a.x << 16); h[t][1] = __uint_as_float(a.x & 0xffff0000u);
+        h[t][2] = __uint_as_float(a.y << 16); h[t][3] = __uint_as_float(a.y & 0xffff0000u);
+      }
+    }
+    // ---- flow = W8 h8 + b8: per-lane partial dot products, xor tree (every lane ends with the sums)
+    float f[4][3];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float acc = w[k][0] * h[t][0];
+        acc = fmaf(w[k][1], h[t][1], acc); acc = fmaf(w[k][2], h[t][2], acc); acc = fmaf(w[k][3], h[t][3], acc);
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(FULL, acc, sft);
+        f[t][k] = acc;
+      }
+    // ---- trilinear lookup of point i0 + q, corner `corner`
+    const int i = i0 + q;
+    const bool live = i < b.n;
+    const float f0 = (q == 0 ? f[0][0] : q == 1 ? f[1][0] : q == 2 ? f[2][0] : f[3][0]) + b8x;
+    const float f1 = (q == 0 ? f[0][1] : q == 1 ? f[1][1] : q == 2 ? f[2][1] : f[3][1]) + b8y;
+    const float f2 = (q == 0 ? f[0][2] : q == 1 ? f[1][2] : q == 2 ? f[2][2] : f[3][2]) + b8z;
+    const float4 x = b.x4[i];
+    const float Y[3] = {x.x + f0, x.y + f1, x.z + f2};
+    // DT.torch_bilinear_distance (fastnsf.py:59-80) followed by grid_sample's own un-normalisation
+    float pass[3], fr[3];
+    int c0[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float sz = (float)(vol.dims[k] - 1);
+      const float raw = __fmul_rn(__fsub_rn(Y[k], vol.lo[k]), vol.gf);
+      const float sc = fminf(fmaxf(raw, 0.f), sz);
+      pass[k] = (raw >= 0.f && raw <= sz) ? vol.gf : 0.f;          // d clip / dY
+      const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, sc), sz), 1.f);
+      const float ixk = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), sz);
+      const float fl = floorf(ixk);
+      c0[k] = (int)fl;
+      fr[k] = ixk - fl;
+    }
+    const int dx = corner >> 2, dy = (corner >> 1) & 1, dz = corner & 1;
+    const int cx = c0[0] + dx, cy = c0[1] + dy, cz = c0[2] + dz;
+    float dv = 0.f;   // zero padding outside the volume
+    if (cx >= 0 && cx < vol.dims[0] && cy >= 0 && cy < vol.dims[1] && cz >= 0 && cz < vol.dims[2])
+      dv = __ldg(D + ((size_t)cx * vol.dims[1] + cy) * vol.dims[2] + cz);
+    const float wx = dx ? fr[0] : 1.f - fr[0], wy = dy ? fr[1] : 1.f - fr[1], wz = dz ? fr[2] : 1.f - fr[2];
+    float val = dv * (wx * wy * wz);
+    float gx = dv * ((dx ? 1.f : -1.f) * wy * wz), gy = dv * ((dy ? 1.f : -1.f) * wx * wz), gz = dv * ((dz ? 1.f : -1.f) * wx * wy);
+#pragma unroll
+    for (int sft = 4; sft > 0; sft >>= 1) {               // the 8 corners of a point sit in 8 adjacent lanes
+      val += __shfl_xor_sync(FULL, val, sft); gx += __shfl_xor_sync(FULL, gx, sft);
+      gy += __shfl_xor_sync(FULL, gy, sft); gz += __shfl_xor_sync(FULL, gz, sft);
+    }
+    // d ix / dY = (sz/2) * (2/sz) * gf * [inside] = gf * [inside]
+    const float d0 = live ? gx * pass[0] * sN : 0.f, d1 = live ? gy * pass[1] * sN : 0.f, d2 = live ? gz * pass[2] * sN : 0.f;
+    if (!live) val = 0.f;
+    if (live && corner == 0) *(float4*)(b.flow + 4 * (size_t)i) = make_float4(f0, f1, f2, val);
+    // ---- back through the output layer: every lane needs (d, val) of all four points
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float e0 = __shfl_sync(FULL, d0, t * 8), e1 = __shfl_sync(FULL, d1, t * 8), e2 = __shfl_sync(FULL, d2, t * 8);
+      const float ev = __shfl_sync(FULL, val, t * 8);
+      a0 += e0; a1 += e1; a2 += e2; a3 += ev;
+      const long long it = i0 + t;
+      float dh[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float g = fmaf(e2, w[2][u], fmaf(e1, w[1][u], e0 * w[0][u]));
+        dh[u] = h[t][u] > 0.f ? g : 0.f;
+      }
+      uint32_t ph[2], pl[2];
+      umma::pack_split2(dh[0], dh[1], split, ph[0], pl[0]);
+      umma::pack_split2(dh[2], dh[3], split, ph[1], pl[1]);
+      *(uint2*)(b.DL[8] + it * 128 + lane * 4) = make_uint2(ph[0], ph[1]);
+      if (split) *(uint2*)(b.DL[8] + b.ps + it * 128 + lane * 4) = make_uint2(pl[0], pl[1]);
+      // d16 row (dflow_x, dflow_y, dflow_z, 0...): 64 bytes per plane, lanes 0..3 the hi row, 4..7 the lo row
+      if (lane < (split ? 8 : 4)) {
+        uint32_t hi[2], lo[2];
+        umma::pack_split2(e0, e1, split, hi[0], lo[0]);
+        umma::pack_split2(e2, 0.f, split, hi[1], lo[1]);
+        const bool lo_row = lane >= 4;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if ((lane & 3) == 0) v = lo_row ? make_uint4(lo[0], lo[1], 0u, 0u) : make_uint4(hi[0], hi[1], 0u, 0u);
+        *((uint4*)(b.d16 + (lo_row ? (size_t)b.n_pad * 32 : 0) + (size_t)it * 32) + (lane & 3)) = v;
+      }
+    }
+  }
+  // per-block partial sums of db8 [3] and the loss (a* are identical in every lane of a warp)
+  if (lane == 0) { red[warp][0] = a0; red[warp][1] = a1; red[warp][2] = a2; red[warp][3] = a3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float sm = 0.f;
+    for (int wv = 0; wv < kHeadThreads / 32; ++wv) sm += red[wv][threadIdx.x];
+    b.head_part[(size_t)blockIdx.x * kHeadPart + threadIdx.x] = sm;
+  }
+}
+
 // loss reduction + best-flow bookkeeping + EarlyStopping.step (nsfp_module.py:65-82), single thread.
 __global__ void k_nsf_control(NsfBufs b, int head_blocks, float min_delta, int patience) {
   if (blockIdx.x != 0 || threadIdx.x >= 32) return;
@@ -1576,6 +1709,8 @@ extern "C" int himo_nsf_volume_geometry(const float* pc0, int n0, const float* p
   return HIMO_OK;
 }
 
+static int g_nsf_head_warp = 1;
+extern "C" int himo_nsf_set_head_warp(int enable) { g_nsf_head_warp = enable ? 1 : 0; return HIMO_OK; }
 static int g_dt_cluster = 1;
 static int g_dt_big_tiles = 3;   // variant of the tiled pass on planes of >= 256 k cells; per axis-2 direction at 1040 x 1030 x 52:
                                  // 0 = 16x16 tiles x 16 planes 1.90 ms, 1 = 32x32 x 16: 3.87, 2 = 16x16 x 8: 1.41, 3 = 16x16 x 4: 1.28
@@ -1739,7 +1874,9 @@ extern "C" int himo_nsf_optimize(const himo_nsf_desc* d, void* stream_) {
 
   auto iteration = [&]() -> int {
     HIMO_RET(nsf_forward_hidden(b, ad, stream));
-    k_nsf_head<<<head_blocks, kHeadThreads, 0, stream>>>(b, d->D, vol); HIMO_LAUNCH_RET();
+    if (g_nsf_head_warp) k_nsf_head_warp<<<head_blocks, kHeadThreads, 0, stream>>>(b, d->D, vol);
+    else k_nsf_head<<<head_blocks, kHeadThreads, 0, stream>>>(b, d->D, vol);
+    HIMO_LAUNCH_RET();
     k_nsf_control<<<1, 32, 0, stream>>>(b, head_blocks, d->min_delta, d->patience); HIMO_LAUNCH_RET();
     k_nsf_snapshot<<<min(ceil_div(n, 256), kNumSMs * 4), 256, 0, stream>>>(b); HIMO_LAUNCH_RET();
     HIMO_RET(nsf_backward_hidden(b, ad, L.dW_part, splits, k_split, stream));

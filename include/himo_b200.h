@@ -364,6 +364,9 @@ size_t himo_nsf_workspace_bytes(int n_max, int planes);
 /* A/B knob: 0 runs the seven hidden layers of the prior as GEMM launches (7 forward + 7 backward per iteration) instead of
  * the two fused chain kernels (k_mlp_chain: a 256-point tile stays in shared memory across the layers; default 1). */
 int himo_nsf_set_fused(int enable);
+/* 1 (default): the FastNSF head (output layer, trilinear lookup, delta_8) runs one warp per point with coalesced rows
+ * (k_nsf_head_warp); 0: one thread per point (k_nsf_head).  Same results up to the order of the fp32 sums. */
+int himo_nsf_set_head_warp(int enable);
 /* 1 (default): the axis-0 / axis-1 raster passes of himo_nsf_dt_build run as one thread-block-cluster launch each
  * (k_nsf_dt_sweep: halo rows exchanged through distributed shared memory, one cluster barrier per plane); 0: the tiled
  * multi-launch passes.  Bit-identical results. */
