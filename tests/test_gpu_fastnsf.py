@@ -191,3 +191,46 @@ def test_engine_pairs_in_flight_equal_one_at_a_time():
     for x, y in zip(one, many):
         assert x.shape == y.shape
         np.testing.assert_array_equal(x, y)
+
+
+def test_dt_big_plane_variants_are_identical():
+    """The tiled raster pass on planes of >= 256 k cells (the axis-2 pass) in its four tilings: bit-identical volumes."""
+    from himo_b200 import _lib
+    rng = np.random.default_rng(21)
+    pc = torch.from_numpy(((rng.random((6000, 3)) - 0.5) * np.array([52.0, 52.0, 0.6])).astype(np.float32))
+    lo, dims = fastnsf.volume_geometry((pc + 0.05).cuda(), pc.cuda(), GF)
+    assert dims[0] * dims[1] >= 1 << 18
+    L = _lib.lib()
+    vols = []
+    try:
+        for variant in (0, 1, 2, 3):
+            L.himo_nsf_set_dt_big_tiles(variant)
+            vols.append(fastnsf.dt_build(pc.cuda(), lo, dims, GF).cpu())
+    finally:
+        L.himo_nsf_set_dt_big_tiles(3)
+    for v in vols[1:]:
+        assert torch.equal(v, vols[0])
+
+
+def test_head_warp_per_point_equals_thread_per_point():
+    """k_nsf_head_warp against k_nsf_head on the same pair and prior: same flow and loss up to the order of the fp32 sums."""
+    from himo_b200 import _lib
+    pc0, pc1 = _pair(9000, 8)
+    sd = weights.synth_neural_prior_state_dict(8)
+    lo, dims = fastnsf.volume_geometry(pc0.cuda(), pc1.cuda(), GF)
+    D = fastnsf.dt_build(pc1.cuda(), lo, dims, GF)
+    L = _lib.lib()
+    outs = []
+    try:
+        for mode in (0, 1):
+            L.himo_nsf_set_head_warp(mode)
+            net = fastnsf.FastNSF(itr_num=3, early_patience=0)
+            outs.append(net.optimize(pc0.cuda(), pc1.cuda(), init_state_dict=sd, D=D, lo=lo, dims=dims, return_params=True))
+    finally:
+        L.himo_nsf_set_head_warp(1)
+    a, b = outs
+    assert a["iterations"] == b["iterations"] == 3
+    assert abs(a["loss"] - b["loss"]) <= 1e-6 * max(1.0, abs(a["loss"]))
+    assert (a["flow"] - b["flow"]).abs().max().item() <= 1e-5
+    # (parameters are not compared entry by entry: Adam turns a noise-level gradient whose sign flips in the last bit into a
+    #  full +-lr step, so a handful of the 116 k entries differ by up to 3 lr while flow and loss agree)
