@@ -147,7 +147,10 @@ def fastnsf(dev, frame: Dict, bf16_tflops: float, iters: int = 48) -> Dict:
             "dt_dims": list(dims), "algorithmic_tflops": flops_iter / (ms_iter * 1e-3) / 1e12,
             "frac_of_bf16_peak": flops_iter / (ms_iter * 1e-3) / 1e12 / bf16_tflops,
             "configured_run": {"iterations": int(r2["iterations"]), "seconds": pair_s, "pairs_per_s": 1.0 / pair_s,
-                               "loss": float(r2["loss"])},
+                               "ms_per_iteration_all_in": pair_s * 1e3 / max(1, int(r2["iterations"])),
+                               "loss": float(r2["loss"]),
+                               "note": "one prior: where the early stop lands (34-235 iterations over eight priors) depends on "
+                                       "the prior and on the last bits of the sums; see engine / engine_stream for the mean"},
             "note": "fp32-class (split fp16 x3 MMAs); 0.692 MFLOP/point/iteration algorithmic"}
 
 
