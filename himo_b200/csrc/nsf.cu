@@ -1719,6 +1719,8 @@ extern "C" int himo_nsf_volume_geometry(const float* pc0, int n0, const float* p
   return HIMO_OK;
 }
 
+static int g_nsf_blocking_poll = 0;
+extern "C" int himo_nsf_set_blocking_poll(int enable) { g_nsf_blocking_poll = enable ? 1 : 0; return HIMO_OK; }
 static int g_nsf_head_warp = 1;
 extern "C" int himo_nsf_set_head_warp(int enable) { g_nsf_head_warp = enable ? 1 : 0; return HIMO_OK; }
 static int g_dt_cluster = 1;
@@ -1897,14 +1899,28 @@ extern "C" int himo_nsf_optimize(const himo_nsf_desc* d, void* stream_) {
   NsfCtl hc = {};
   const int poll = d->poll_iters > 0 ? d->poll_iters : 8;
   int launched = 0;
+  // The host waits for every chunk on a BLOCKING-sync event (the thread sleeps instead of spinning in
+  // cudaStreamSynchronize): several pairs are optimised from worker threads of one process, one process per GPU, and
+  // spinning pollers would take a host core each for the whole run.
+  // (himo_nsf_set_blocking_poll(1), set by FastNSFEngine.infer_stream; a lone optimiser keeps the spinning wait: the sleeping
+  //  one costs ~0.05 ms per iteration in wake-up latency, 0.49 -> 0.54 ms)
+  cudaEvent_t chunk_done = nullptr;
+  HIMO_CUDA_RET(cudaEventCreateWithFlags(&chunk_done, (g_nsf_blocking_poll ? cudaEventBlockingSync : 0) | cudaEventDisableTiming));
+  int loop_status = HIMO_OK;
   while (launched < d->max_iters) {
     const int chunk = (d->max_iters - launched) < poll ? (d->max_iters - launched) : poll;
-    for (int k = 0; k < chunk; ++k) HIMO_RET(iteration());
+    for (int k = 0; k < chunk && loop_status == HIMO_OK; ++k) loop_status = iteration();
+    if (loop_status != HIMO_OK) break;
     launched += chunk;
-    HIMO_CUDA_RET(cudaMemcpyAsync(&hc, b.ctl, sizeof(NsfCtl), cudaMemcpyDeviceToHost, stream));
-    HIMO_CUDA_RET(cudaStreamSynchronize(stream));
+    cudaError_t ce = cudaEventRecord(chunk_done, stream);
+    if (ce == cudaSuccess) ce = cudaEventSynchronize(chunk_done);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&hc, b.ctl, sizeof(NsfCtl), cudaMemcpyDeviceToHost, stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream);
+    if (ce != cudaSuccess) { loop_status = (int)ce; break; }     // > 0: cudaError_t, as everywhere in this ABI
     if (hc.stop) break;
   }
+  cudaEventDestroy(chunk_done);
+  if (loop_status != HIMO_OK) return loop_status;
   k_nsf_unpack_flow<<<min(ceil_div(n, 256), kNumSMs * 4), 256, 0, stream>>>(b.best_flow, n, d->best_flow);
   HIMO_LAUNCH_RET();
   if (d->final_params)

@@ -258,6 +258,7 @@ class FastNSFEngine:
                 yield self.infer(frame)
             return
         from concurrent.futures import ThreadPoolExecutor
+        _lib.lib().himo_nsf_set_blocking_poll(1)       # the workers sleep while their chunk of iterations runs (process-wide knob)
         if self._lanes is None:
             self._lanes = [(self.net if k == 0 else self._make_net(), torch.cuda.Stream(self.device))
                            for k in range(self.n_workers)]
@@ -286,6 +287,7 @@ class FastNSFEngine:
                 lane, out, its = pending.pop(0).result()
                 self.last_iterations.append(its)
                 yield out
+        _lib.lib().himo_nsf_set_blocking_poll(0)
 
 
 class NSFPEngine(FastNSFEngine):

@@ -43,6 +43,7 @@ _lib.register("himo_nsf_optimize", c_int, [ctypes.POINTER(_NsfDesc), c_void_p])
 _lib.register("himo_nsf_set_dt_cluster", c_int, [c_int])
 _lib.register("himo_nsf_set_dt_big_tiles", c_int, [c_int])
 _lib.register("himo_nsf_set_head_warp", c_int, [c_int])
+_lib.register("himo_nsf_set_blocking_poll", c_int, [c_int])
 _lib.register("himo_nsf_dt_pass", c_int, [c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p])
 
 

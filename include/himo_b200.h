@@ -367,6 +367,10 @@ int himo_nsf_set_fused(int enable);
 /* 1 (default): the FastNSF head (output layer, trilinear lookup, delta_8) runs one warp per point with coalesced rows
  * (k_nsf_head_warp); 0: one thread per point (k_nsf_head).  Same results up to the order of the fp32 sums. */
 int himo_nsf_set_head_warp(int enable);
+/* 1: himo_nsf_optimize waits for each chunk of iterations on a blocking-sync event (the calling thread sleeps); 0 (default):
+ * it spins.  Set by FastNSFEngine.infer_stream, which optimises several pairs from worker threads: spinning pollers would
+ * each take a host core for the whole run.  Costs ~0.05 ms per iteration in wake-up latency for a lone optimiser. */
+int himo_nsf_set_blocking_poll(int enable);
 /* 1 (default): the axis-0 / axis-1 raster passes of himo_nsf_dt_build run as one thread-block-cluster launch each
  * (k_nsf_dt_sweep: halo rows exchanged through distributed shared memory, one cluster barrier per plane); 0: the tiled
  * multi-launch passes.  Bit-identical results. */
