@@ -1,6 +1,6 @@
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 50 --warmup 3 > gpurun_out/r02_c31_bench2.json 2> gpurun_out/r02_c31_bench2.err; echo bench2=$?
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus ${NG:-2} --steps 50 --warmup 3 > gpurun_out/r02_c31_bench2.json 2> gpurun_out/r02_c31_bench2.err; echo bench2=$?
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/r02_c31_bench2.json').read().strip().splitlines()[-1])
@@ -12,4 +12,4 @@ print('fastnsf', {k: d['fastnsf'].get(k) for k in ('ms_per_iter','dt_build_ms','
 print('knn', d['knn'].get('lidar_100k'), d['knn'].get('uniform_1m'))
 PY
 tail -3 gpurun_out/r02_c31_bench2.err
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 | cut -c1-600
+
